@@ -1,0 +1,27 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """Vectors produced by the reference's own code (tests/golden/make_golden.py)."""
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_golden.npz"))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _build_oracle():
+    """The C checkers are built on demand (gcc only); the product never loads them."""
+    import subprocess
+    if not os.path.exists(os.path.join(ROOT, "oracle", "libfsport.so")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)

@@ -1,0 +1,138 @@
+"""CPU tests: the oracle (oracle/) against the golden vectors produced by the reference's own code."""
+import numpy as np
+import pytest
+
+from oracle import ffi_oracle as O
+
+
+def _fs_cases(golden):
+    for i in range(int(golden["fs_ncases"])):
+        nd, ns, nuc_dip, nuc_strike = (int(v) for v in golden[f"fs{i}_meta"])
+        yield i, nd, ns, nuc_dip, nuc_strike, float(golden[f"fs{i}_h"]), golden[f"fs{i}_slow"]
+
+
+def test_fast_sweep_port_vs_reference_c(golden):
+    """Plain-C restatement vs the reference's compiled C: <= 2 ulp (glibc pow(x,.5) vs sqrt), identical indices."""
+    for i, nd, ns, nuc_dip, nuc_strike, h, slow in _fs_cases(golden):
+        t = O.fast_sweep(slow, h, nuc_dip, nuc_strike, nd, ns, impl="port")
+        ref = golden[f"fs{i}_t_c"]
+        assert np.all(np.abs(t - ref) <= 4 * np.spacing(np.abs(ref))), i
+        # the reference's own cross-implementation gate (test/test_fastsweep.py:131-133)
+        np.testing.assert_allclose(t, golden[f"fs{i}_t_numpy"], rtol=0, atol=1e-6)
+        for interp in ("nearest_neighbor", "multilinear"):
+            a, _ = O.times2idxs(t, -5.0, 0.5, interp)
+            b, _ = O.times2idxs(ref, -5.0, 0.5, interp)
+            assert np.array_equal(a, b)
+
+
+def test_fast_sweep_kat_reference_test_case(golden):
+    """Known-answer: reference test inputs (test/test_fastsweep.py:21-31); values as in BASELINE.md."""
+    t = O.fast_sweep(golden["fs0_slow"], 10.0, 3, 2, 6, 4, impl="port").reshape(6, 4)
+    np.testing.assert_allclose(t[3], [20.0, 10.0, 0.0, 2.8571428571428568], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(t[0], [27.757645028504108, 18.1593235621289, 8.57142857142857, 9.834944019440146],
+                               rtol=0, atol=1e-13)
+
+
+def test_fast_sweep_ref_binary_if_present(golden):
+    if O.load_reference_ext() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    for i, nd, ns, nuc_dip, nuc_strike, h, slow in _fs_cases(golden):
+        t = O.fast_sweep(slow, h, nuc_dip, nuc_strike, nd, ns, impl="ref")
+        assert np.array_equal(t, golden[f"fs{i}_t_c"])
+
+
+def test_port_vs_ref_random_grids():
+    """Wider sweep of random grids, only where the reference binary is available."""
+    if O.load_reference_ext() is None:
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(3)
+    nbit = 0
+    for _ in range(400):
+        nd, ns = int(rng.integers(1, 24)), int(rng.integers(1, 40))
+        slow = 1.0 / rng.uniform(2.2, 4.5, nd * ns)
+        hr, hc = int(rng.integers(0, nd)), int(rng.integers(0, ns))
+        h = float(rng.choice([1.0, 2.0, 2.5, 5.0]))
+        a = O.fast_sweep(slow, h, hr, hc, nd, ns, impl="ref")
+        b = O.fast_sweep(slow, h, hr, hc, nd, ns, impl="port")
+        assert np.all(np.abs(a - b) <= 4 * np.spacing(np.abs(a)))
+        nbit += np.array_equal(a, b)
+        ia, _ = O.times2idxs(a, -5.0, 0.5, "nearest_neighbor")
+        ib, _ = O.times2idxs(b, -5.0, 0.5, "nearest_neighbor")
+        assert np.array_equal(ia, ib)
+    assert nbit >= 380
+
+
+def test_positions2idxs(golden):
+    for cs in (1.0, 2.0, 2.5):
+        got = O.positions2idxs(golden["pos_in"], cs)
+        assert got.dtype == np.int16
+        assert np.array_equal(got, golden[f"pos_idx_{cs}"])
+
+
+@pytest.mark.parametrize("name", ["rand", "recipe"])
+@pytest.mark.parametrize("tag,interp", [("nn", "nearest_neighbor"), ("ml", "multilinear")])
+def test_stack_all(golden, name, tag, interp):
+    st_min, st_step, dur_min, dur_step = golden["stack_axes"]
+    G = golden[f"stack_{name}_G"]
+    d, s, u = golden[f"stack_{name}_durations"], golden[f"stack_{name}_starttimes"], golden[f"stack_{name}_slips"]
+    got = O.stack_all(G, d, s, u, dur_min, dur_step, st_min, st_step, interp)
+    ref = golden[f"stack_{name}_{tag}"]
+    np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-13 * np.abs(ref).max())
+    loops = O.stack_all_loops(G, d, s, u, dur_min, dur_step, st_min, st_step, interp)
+    np.testing.assert_allclose(loops, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    si, sf = O.times2idxs(s, st_min, st_step, interp)
+    di, df = O.times2idxs(d, dur_min, dur_step, interp)
+    assert np.array_equal(si, golden[f"stack_{name}_{tag}_si"]) and si.dtype == np.int16
+    assert np.array_equal(di, golden[f"stack_{name}_{tag}_di"])
+    if interp == "multilinear":
+        assert np.array_equal(sf, golden[f"stack_{name}_{tag}_sf"])
+        assert np.array_equal(df, golden[f"stack_{name}_{tag}_df"])
+
+
+def test_geodetic_stack(golden):
+    np.testing.assert_allclose(O.geodetic_stack_all(golden["geo_G"], golden["geo_slips"]), golden["geo_mu"],
+                               rtol=1e-14, atol=1e-14)
+
+
+def test_covariance_and_mvn(golden):
+    C, U, lp = golden["mvn_C"], golden["mvn_U"], golden["mvn_logpdet"]
+    n_t, ns = C.shape[0], C.shape[1]
+    for i in range(n_t):
+        np.testing.assert_allclose(O.chol_inverse(C[i]), U[i], rtol=1e-10, atol=1e-10 * np.abs(U[i]).max())
+        np.testing.assert_allclose(O.log_pdet(C[i]), lp[i], rtol=1e-13)
+    res = golden["mvn_res"]
+    got = O.mvn_chol_logpts(res, U, lp, [ns] * n_t, float(golden["mvn_h_scalar"]))
+    np.testing.assert_allclose(got, golden["mvn_logpts_scalar"], rtol=1e-13)
+    got = O.mvn_chol_logpts(res, U, lp, [ns] * n_t, golden["mvn_h_vec"])
+    np.testing.assert_allclose(got, golden["mvn_logpts_vec"], rtol=1e-13)
+    np.testing.assert_array_equal(O.exponential_data_covariance(16, 0.5, 2.0), golden["cov_exp_n16"])
+
+
+def test_mvn_vs_scipy():
+    """Property the reference tests (test/test_models.py:149-222): llk == scipy logpdf of N(0, C e^{2h})."""
+    import scipy.stats
+    rng = np.random.default_rng(1)
+    ns = 40
+    C = O.exponential_data_covariance(ns, 0.5, 2.0) * 0.3 ** 2
+    U, lp = O.chol_inverse(C), O.log_pdet(C)
+    r = rng.standard_normal(ns)
+    for h in (0.0, 0.7, -0.4):
+        got = O.mvn_chol_logpts([r], [U], [lp], [ns], h)[0]
+        ref = scipy.stats.multivariate_normal.logpdf(r, mean=np.zeros(ns), cov=C * np.exp(2 * h))
+        assert abs(got - ref) < 1e-9 * abs(ref)
+
+
+def test_exponential_U_is_bidiagonal():
+    """chol(inv(C_exponential)).T is upper-bidiagonal to ~1e-14 -- basis of the banded misfit path."""
+    for n, dt, t0 in ((120, 0.5, 2.0), (128, 0.5, 2.0), (64, 1.0, 5.0)):
+        U = O.chol_inverse(O.exponential_data_covariance(n, dt, t0) * 0.01)
+        off = U - np.diag(np.diag(U)) - np.diag(np.diag(U, 1), 1)
+        assert np.abs(off).max() < 1e-12 * np.abs(U).max()
+
+
+def test_laplacian(golden):
+    nstr, ndip, hs, hd = golden["lap_dims"]
+    L = O.smoothing_operator_nearest_neighbor(int(nstr), int(ndip), hs, hd)
+    np.testing.assert_array_equal(L, golden["lap_L"])
+    got = O.laplacian_logpt(L, float(golden["lap_sdet"]), golden["lap_u"], float(golden["lap_h"]))
+    np.testing.assert_allclose(got, float(golden["lap_logpt"]), rtol=1e-14)
