@@ -1,0 +1,995 @@
+// beatgpu.cu -- host side of libbeatgpu.so: context, operand upload, kernel launches, the extern "C" ABI
+//               declared in include/beatgpu.h.  sm_100a only; no CPU fallback anywhere.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "beatgpu.h"
+#include "sweep.cuh"
+#include "stack.cuh"
+#include "aux.cuh"
+
+using namespace beatgpu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct WaveMap {
+    int nt = 0, ns = 0, interp = 0;
+    bool has_station = false;
+    int* d_station_idx = nullptr;
+    int* d_hyper_idx = nullptr;
+    int* d_nsamp = nullptr;
+    // library
+    void* G[BEATGPU_MAX_SLIPVARS] = {nullptr, nullptr, nullptr};
+    bool G_owned[BEATGPU_MAX_SLIPVARS] = {false, false, false};
+    int store_dtype = -1;
+    int64_t dims[5] = {0, 0, 0, 0, 0};
+    long ld = 0;
+    double dur_min = 0, dur_step = 1, st_min = 0, st_step = 1;
+    bool axes_set = false;
+    // data / weights
+    double* d_data = nullptr;
+    double* d_W = nullptr;
+    size_t W_bytes = 0;
+    double* d_slog_pdet = nullptr;
+    int misfit_mode = -1, bw = 0, dense_upper = 1;
+    int out_ofs = 0;
+};
+
+struct Geodetic {
+    bool set = false;
+    int nobs = 0, nds = 0, max_n = 0;
+    double* G[BEATGPU_MAX_SLIPVARS] = {nullptr, nullptr, nullptr};
+    double *d_data = nullptr, *d_odw = nullptr, *d_UT = nullptr, *d_slog = nullptr;
+    long* d_UT_ofs = nullptr;
+    int *d_lo = nullptr, *d_hi = nullptr, *d_upper = nullptr, *d_nsamp = nullptr, *d_hyper_idx = nullptr;
+    std::vector<int> lo, hi;
+    std::vector<long> ut_ofs;
+    long ut_total = 0;
+    int out_ofs = 0;
+};
+
+struct Laplacian {
+    bool set = false;
+    double* d_LT = nullptr;
+    double sdet = 0;
+    int hyper_idx = 0;
+    int out_ofs = 0;
+};
+
+}  // namespace
+
+struct beatgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    std::string err;
+    cudaDeviceProp prop;
+    // fault
+    int nsf = 0, np_total = 0, max_np_sf = 0;
+    std::vector<int> h_nd, h_ns, h_pofs;
+    std::vector<double> h_psize;
+    int *d_nd = nullptr, *d_ns = nullptr, *d_pofs = nullptr;
+    double* d_psize = nullptr;
+    // layout
+    bool layout_set = false;
+    beatgpu_layout layout;
+    double* d_fixed = nullptr;
+    long canon_slip[BEATGPU_MAX_SLIPVARS], canon_dur = 0, canon_vel = 0, canon_nstr = 0, canon_ndip = 0, canon_time = 0,
+         canon_hyp = 0, canon_ts = 0, canon_len = 0;
+    // composites
+    std::vector<WaveMap> wmaps;
+    Geodetic geo;
+    Laplacian lap;
+    // scratch (grown on demand)
+    int cap_B = 0;
+    double* d_q = nullptr;          // [cap_B, n_params]  (host-entry staging)
+    double* d_logpts = nullptr;     // [cap_B, n_out]
+    double* d_like = nullptr;       // [cap_B]
+    double* d_t0 = nullptr;         // [cap_B, np_total]
+    unsigned char* d_bad = nullptr; // [cap_B]
+    int cap_n_out = 0, cap_n_params = 0;
+    unsigned long long* d_viol = nullptr;
+    // generic scratch for the unit entries
+    void* d_tmp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t tmp_bytes[6] = {0, 0, 0, 0, 0, 0};
+    // accounting
+    long long n_launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool ev_valid = false;
+};
+
+namespace {
+
+int fail(beatgpu_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(ctx, BEATGPU_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                          \
+    } while (0)
+
+#define CKL()                                                                                          \
+    do {                                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                                          \
+        if (e__ != cudaSuccess)                                                                        \
+            return fail(ctx, BEATGPU_E_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                                           \
+        ctx->n_launches++;                                                                             \
+    } while (0)
+
+template <typename T>
+int upload_vec(beatgpu_ctx* ctx, T** dptr, const T* h, size_t n)
+{
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    if (n == 0) return BEATGPU_OK;
+    CK(cudaMalloc((void**)dptr, n * sizeof(T)));
+    CK(cudaMemcpyAsync(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BEATGPU_OK;
+}
+
+int ensure_tmp(beatgpu_ctx* ctx, int slot, size_t bytes)
+{
+    if (ctx->tmp_bytes[slot] >= bytes) return BEATGPU_OK;
+    if (ctx->d_tmp[slot]) cudaFree(ctx->d_tmp[slot]);
+    ctx->d_tmp[slot] = nullptr;
+    ctx->tmp_bytes[slot] = 0;
+    CK(cudaMalloc(&ctx->d_tmp[slot], bytes));
+    ctx->tmp_bytes[slot] = bytes;
+    return BEATGPU_OK;
+}
+
+int n_outputs(const beatgpu_ctx* ctx)
+{
+    int n = 0;
+    for (const auto& w : ctx->wmaps) n += w.nt;
+    if (ctx->geo.set) n += ctx->geo.nds;
+    if (ctx->lap.set) n += 1;
+    return n;
+}
+
+void assign_out_offsets(beatgpu_ctx* ctx)
+{
+    int o = 0;
+    for (auto& w : ctx->wmaps) { w.out_ofs = o; o += w.nt; }
+    ctx->geo.out_ofs = o;
+    if (ctx->geo.set) o += ctx->geo.nds;
+    ctx->lap.out_ofs = o;
+}
+
+int ensure_scratch(beatgpu_ctx* ctx, int B)
+{
+    const int n_out = std::max(1, n_outputs(ctx));
+    const int n_par = ctx->layout_set ? ctx->layout.n_params : 1;
+    if (B <= ctx->cap_B && n_out <= ctx->cap_n_out && n_par <= ctx->cap_n_params) return BEATGPU_OK;
+    const int nb = std::max(B, ctx->cap_B);
+    cudaFree(ctx->d_q); cudaFree(ctx->d_logpts); cudaFree(ctx->d_like); cudaFree(ctx->d_t0); cudaFree(ctx->d_bad);
+    ctx->d_q = ctx->d_logpts = ctx->d_like = ctx->d_t0 = nullptr;
+    ctx->d_bad = nullptr;
+    ctx->cap_B = 0;
+    CK(cudaMalloc((void**)&ctx->d_q, (size_t)nb * n_par * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->d_logpts, (size_t)nb * n_out * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->d_like, (size_t)nb * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->d_t0, (size_t)nb * std::max(1, ctx->np_total) * sizeof(double)));
+    CK(cudaMalloc((void**)&ctx->d_bad, (size_t)nb));
+    ctx->cap_B = nb;
+    ctx->cap_n_out = n_out;
+    ctx->cap_n_params = n_par;
+    return BEATGPU_OK;
+}
+
+// pointer + per-chain stride of a model variable inside q (or the fixed vector)
+struct VarRef { const double* p; long stride; };
+VarRef var_ref(const beatgpu_ctx* ctx, const double* q_dev, int off, long canon)
+{
+    if (off >= 0) return {q_dev + off, (long)ctx->layout.n_params};
+    return {ctx->d_fixed + canon, 0};
+}
+
+int launch_sweep(beatgpu_ctx* ctx, SweepArgs& a, int n_items)
+{
+    size_t per_warp = (size_t)4 * a.max_np_sf * sizeof(double);
+    int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (48 * 1024) / per_warp));
+    size_t smem = per_warp * wpb;
+    if (smem > 48 * 1024) {
+        if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
+            return fail(ctx, BEATGPU_E_ARG, "subfault of %d patches needs %zu B shared memory per warp (> %zu)",
+                        a.max_np_sf, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
+        CK(cudaFuncSetAttribute(chain_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int blocks = (n_items + wpb - 1) / wpb;
+    chain_sweep_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(a, wpb);
+    CKL();
+    return BEATGPU_OK;
+}
+
+template <typename T, int K, bool WS>
+int launch_stack_nvar(beatgpu_ctx* ctx, const StackArgs& a)
+{
+    const size_t smem = WS ? 0 : (size_t)a.ns * sizeof(double);
+    const long grid = (long)a.nt * a.B;
+    if (grid > 2147483647L) return fail(ctx, BEATGPU_E_ARG, "grid too large: nt*B = %ld", grid);
+#define LAUNCH(NV)                                                                                                   \
+    do {                                                                                                             \
+        if (smem > 48 * 1024)                                                                                        \
+            CK(cudaFuncSetAttribute(gf_stack_misfit_kernel<T, K, NV, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        gf_stack_misfit_kernel<T, K, NV, WS><<<(unsigned)grid, kStackThreads, smem, ctx->stream>>>(a);              \
+    } while (0)
+    switch (a.nvar) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 3: LAUNCH(3); break;
+        default: return fail(ctx, BEATGPU_E_ARG, "n_slipvars must be 1..3, got %d", a.nvar);
+    }
+#undef LAUNCH
+    CKL();
+    return BEATGPU_OK;
+}
+
+template <bool WS>
+int launch_stack(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
+{
+    if (a.ns > 16384) return fail(ctx, BEATGPU_E_ARG, "nsamples %d too large", a.ns);
+    if (w.store_dtype == BEATGPU_F32) {
+        return (w.interp == BEATGPU_NEAREST) ? launch_stack_nvar<float, 1, WS>(ctx, a) : launch_stack_nvar<float, 4, WS>(ctx, a);
+    } else {
+        return (w.interp == BEATGPU_NEAREST) ? launch_stack_nvar<double, 1, WS>(ctx, a) : launch_stack_nvar<double, 4, WS>(ctx, a);
+    }
+}
+
+void fill_static(const WaveMap& w, StackArgs& a, int nvar)
+{
+    a.nvar = nvar;
+    for (int v = 0; v < BEATGPU_MAX_SLIPVARS; ++v) a.G[v] = w.G[v];
+    a.nt = w.nt;
+    a.np = (int)w.dims[1];
+    a.ndur = (int)w.dims[2];
+    a.nst = (int)w.dims[3];
+    a.ns = w.ns;
+    a.ld = w.ld;
+    a.dur_min = w.dur_min; a.dur_step = w.dur_step; a.st_min = w.st_min; a.st_step = w.st_step;
+    a.data = w.d_data;
+    a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
+    a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
+    a.hyper_idx = w.d_hyper_idx;
+    a.station_idx = w.d_station_idx;
+}
+
+int check_lib(beatgpu_ctx* ctx, const WaveMap& w, int nvar)
+{
+    for (int v = 0; v < nvar; ++v)
+        if (!w.G[v]) return fail(ctx, BEATGPU_E_NOTREADY, "GF library for slip variable %d not uploaded", v);
+    return BEATGPU_OK;
+}
+
+long row_stride_for(int ns, int store_dtype)
+{
+    long align_bytes = 16;
+    if (const char* e = getenv("BEATGPU_ROW_ALIGN_BYTES")) { long v = atol(e); if (v >= 16 && (v % 16) == 0) align_bytes = v; }
+    const long esz = (store_dtype == BEATGPU_F32) ? 4 : 8;
+    const long bytes = ((long)ns * esz + align_bytes - 1) / align_bytes * align_bytes;
+    return bytes / esz;
+}
+
+int set_lib_meta(beatgpu_ctx* ctx, WaveMap& w, int store_dtype, const int64_t dims[5], double dmin, double dstep,
+                 double smin, double sstep)
+{
+    if (dims[0] != w.nt || dims[4] != w.ns)
+        return fail(ctx, BEATGPU_E_ARG, "library dims (%ld targets, %ld samples) do not match wavemap (%d, %d)",
+                    (long)dims[0], (long)dims[4], w.nt, w.ns);
+    if (ctx->np_total && dims[1] != ctx->np_total)
+        return fail(ctx, BEATGPU_E_ARG, "library has %ld patches, fault has %d", (long)dims[1], ctx->np_total);
+    if (dims[0] * dims[1] * dims[2] * dims[3] > 2147483647LL)
+        return fail(ctx, BEATGPU_E_ARG, "library has more than 2^31 rows");
+    if (!(dstep > 0) || !(sstep > 0)) return fail(ctx, BEATGPU_E_ARG, "axis steps must be positive");
+    if (w.axes_set) {
+        bool same = w.store_dtype == store_dtype && w.dur_min == dmin && w.dur_step == dstep && w.st_min == smin && w.st_step == sstep;
+        for (int i = 0; i < 5; ++i) same = same && (w.dims[i] == dims[i]);
+        if (!same) return fail(ctx, BEATGPU_E_ARG, "all slip components of a wavemap must share dims, axes and storage dtype");
+    }
+    w.store_dtype = store_dtype;
+    for (int i = 0; i < 5; ++i) w.dims[i] = dims[i];
+    w.ld = row_stride_for(w.ns, store_dtype);
+    w.dur_min = dmin; w.dur_step = dstep; w.st_min = smin; w.st_step = sstep;
+    w.axes_set = true;
+    return BEATGPU_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int beatgpu_version(void) { return BEATGPU_VERSION; }
+
+const char* beatgpu_last_error(const beatgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int beatgpu_ctx_create(int device, beatgpu_ctx** out)
+{
+    beatgpu_ctx* ctx = nullptr;
+    if (!out) return fail(nullptr, BEATGPU_E_ARG, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, BEATGPU_E_CUDA, "no CUDA device available (%s); libbeatgpu has no CPU fallback",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, BEATGPU_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    beatgpu_ctx* c = new beatgpu_ctx();
+    c->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&c->d_viol, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMemset(c->d_viol, 0, sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        int rc = fail(nullptr, BEATGPU_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+        delete c;
+        return rc;
+    }
+    if (c->prop.major != 10)
+        fprintf(stderr, "libbeatgpu: warning: built for sm_100a, device is sm_%d%d\n", c->prop.major, c->prop.minor);
+    for (int v = 0; v < BEATGPU_MAX_SLIPVARS; ++v) c->canon_slip[v] = 0;
+    memset(&c->layout, 0, sizeof(c->layout));
+    (void)ctx;
+    *out = c;
+    return BEATGPU_OK;
+}
+
+void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& w : ctx->wmaps) {
+        for (int v = 0; v < BEATGPU_MAX_SLIPVARS; ++v) if (w.G[v] && w.G_owned[v]) cudaFree(w.G[v]);
+        cudaFree(w.d_station_idx); cudaFree(w.d_hyper_idx); cudaFree(w.d_nsamp); cudaFree(w.d_data); cudaFree(w.d_W);
+        cudaFree(w.d_slog_pdet);
+    }
+    Geodetic& g = ctx->geo;
+    for (int v = 0; v < BEATGPU_MAX_SLIPVARS; ++v) cudaFree(g.G[v]);
+    cudaFree(g.d_data); cudaFree(g.d_odw); cudaFree(g.d_UT); cudaFree(g.d_slog); cudaFree(g.d_UT_ofs); cudaFree(g.d_lo);
+    cudaFree(g.d_hi); cudaFree(g.d_upper); cudaFree(g.d_nsamp); cudaFree(g.d_hyper_idx);
+    cudaFree(ctx->lap.d_LT);
+    cudaFree(ctx->d_nd); cudaFree(ctx->d_ns); cudaFree(ctx->d_pofs); cudaFree(ctx->d_psize); cudaFree(ctx->d_fixed);
+    cudaFree(ctx->d_q); cudaFree(ctx->d_logpts); cudaFree(ctx->d_like); cudaFree(ctx->d_t0); cudaFree(ctx->d_bad);
+    cudaFree(ctx->d_viol);
+    for (int i = 0; i < 6; ++i) cudaFree(ctx->d_tmp[i]);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int beatgpu_sync(beatgpu_ctx* ctx)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BEATGPU_OK;
+}
+
+int beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (cuda_stream) {
+        ctx->stream = (cudaStream_t)cuda_stream;
+        ctx->own_stream = false;
+    } else {
+        CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return BEATGPU_OK;
+}
+
+int beatgpu_device_info(beatgpu_ctx* ctx, int* n_sm, char* name, int name_len)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (n_sm) *n_sm = ctx->prop.multiProcessorCount;
+    if (name && name_len > 0) { strncpy(name, ctx->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return BEATGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int beatgpu_set_fault(beatgpu_ctx* ctx, int nsf, const int32_t* nd, const int32_t* ns, const double* psize)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (nsf <= 0 || !nd || !ns || !psize) return fail(ctx, BEATGPU_E_ARG, "set_fault: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    ctx->h_nd.assign(nd, nd + nsf);
+    ctx->h_ns.assign(ns, ns + nsf);
+    ctx->h_psize.assign(psize, psize + nsf);
+    ctx->h_pofs.resize(nsf);
+    int tot = 0, mx = 0;
+    for (int i = 0; i < nsf; ++i) {
+        if (nd[i] <= 0 || ns[i] <= 0 || !(psize[i] > 0)) return fail(ctx, BEATGPU_E_ARG, "set_fault: subfault %d has an empty grid", i);
+        ctx->h_pofs[i] = tot;
+        tot += nd[i] * ns[i];
+        mx = std::max(mx, nd[i] * ns[i]);
+    }
+    ctx->nsf = nsf; ctx->np_total = tot; ctx->max_np_sf = mx;
+    int rc;
+    if ((rc = upload_vec(ctx, &ctx->d_nd, ctx->h_nd.data(), nsf))) return rc;
+    if ((rc = upload_vec(ctx, &ctx->d_ns, ctx->h_ns.data(), nsf))) return rc;
+    if ((rc = upload_vec(ctx, &ctx->d_pofs, ctx->h_pofs.data(), nsf))) return rc;
+    if ((rc = upload_vec(ctx, &ctx->d_psize, ctx->h_psize.data(), nsf))) return rc;
+    ctx->layout_set = false;
+    return BEATGPU_OK;
+}
+
+int beatgpu_set_layout(beatgpu_ctx* ctx, const beatgpu_layout* L, const double* fixed)
+{
+    if (!ctx || !L) return BEATGPU_E_ARG;
+    if (!ctx->nsf) return fail(ctx, BEATGPU_E_NOTREADY, "set_layout: call set_fault first");
+    if (L->n_slipvars < 1 || L->n_slipvars > BEATGPU_MAX_SLIPVARS) return fail(ctx, BEATGPU_E_ARG, "set_layout: n_slipvars %d", L->n_slipvars);
+    if (L->n_params <= 0 || L->n_hypers < 0 || L->n_time_shifts < 0) return fail(ctx, BEATGPU_E_ARG, "set_layout: bad sizes");
+    CK(cudaSetDevice(ctx->device));
+    const int np = ctx->np_total, nsf = ctx->nsf;
+    long o = 0;
+    for (int v = 0; v < L->n_slipvars; ++v) { ctx->canon_slip[v] = o; o += np; }
+    ctx->canon_dur = o; o += np;
+    ctx->canon_vel = o; o += np;
+    ctx->canon_nstr = o; o += nsf;
+    ctx->canon_ndip = o; o += nsf;
+    ctx->canon_time = o; o += nsf;
+    ctx->canon_hyp = o; o += L->n_hypers;
+    ctx->canon_ts = o; o += L->n_time_shifts;
+    ctx->canon_len = o;
+    struct { int off; int len; const char* name; } vars[16];
+    int nv = 0;
+    for (int v = 0; v < L->n_slipvars; ++v) vars[nv++] = {L->off_slip[v], np, "slip"};
+    vars[nv++] = {L->off_durations, np, "durations"};
+    vars[nv++] = {L->off_velocities, np, "velocities"};
+    vars[nv++] = {L->off_nucleation_strike, nsf, "nucleation_strike"};
+    vars[nv++] = {L->off_nucleation_dip, nsf, "nucleation_dip"};
+    vars[nv++] = {L->off_time, nsf, "time"};
+    if (L->n_hypers) vars[nv++] = {L->off_hypers, L->n_hypers, "hypers"};
+    if (L->n_time_shifts) vars[nv++] = {L->off_time_shifts, L->n_time_shifts, "time_shifts"};
+    bool any_fixed = false;
+    for (int i = 0; i < nv; ++i) {
+        if (vars[i].off < 0) { any_fixed = true; continue; }
+        if (vars[i].off + vars[i].len > L->n_params)
+            return fail(ctx, BEATGPU_E_ARG, "set_layout: %s [%d, %d) exceeds n_params %d", vars[i].name, vars[i].off,
+                        vars[i].off + vars[i].len, L->n_params);
+    }
+    if (any_fixed && !fixed) return fail(ctx, BEATGPU_E_ARG, "set_layout: variables with offset -1 need the `fixed` vector");
+    std::vector<double> fx((size_t)std::max<long>(1, ctx->canon_len), 0.0);
+    if (fixed) std::copy(fixed, fixed + ctx->canon_len, fx.begin());
+    int rc = upload_vec(ctx, &ctx->d_fixed, fx.data(), fx.size());
+    if (rc) return rc;
+    ctx->layout = *L;
+    ctx->layout_set = true;
+    return BEATGPU_OK;
+}
+
+int beatgpu_add_wavemap(beatgpu_ctx* ctx, int nt, int ns, int interp, const int32_t* station_idx, const int32_t* hyper_idx,
+                        const int32_t* nsamples, int* wmap_id)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (nt <= 0 || ns <= 0 || !hyper_idx || !nsamples || !wmap_id) return fail(ctx, BEATGPU_E_ARG, "add_wavemap: bad arguments");
+    if (interp != BEATGPU_NEAREST && interp != BEATGPU_MULTILINEAR)
+        return fail(ctx, BEATGPU_E_ARG, "add_wavemap: interpolation scheme %d not implemented", interp);
+    CK(cudaSetDevice(ctx->device));
+    WaveMap w;
+    w.nt = nt; w.ns = ns; w.interp = interp;
+    int rc;
+    if (station_idx) { w.has_station = true; if ((rc = upload_vec(ctx, &w.d_station_idx, station_idx, nt))) return rc; }
+    if ((rc = upload_vec(ctx, &w.d_hyper_idx, hyper_idx, nt))) return rc;
+    if ((rc = upload_vec(ctx, &w.d_nsamp, nsamples, nt))) return rc;
+    ctx->wmaps.push_back(w);
+    *wmap_id = (int)ctx->wmaps.size() - 1;
+    assign_out_offsets(ctx);
+    return BEATGPU_OK;
+}
+
+#define GET_WMAP(id)                                                                                   \
+    if (!ctx) return BEATGPU_E_ARG;                                                                    \
+    if ((id) < 0 || (id) >= (int)ctx->wmaps.size()) return fail(ctx, BEATGPU_E_ARG, "unknown wavemap id %d", (id)); \
+    WaveMap& w = ctx->wmaps[(id)];                                                                     \
+    CK(cudaSetDevice(ctx->device))
+
+int beatgpu_alloc_gflib(beatgpu_ctx* ctx, int wmap_id, int var, int store_dtype, const int64_t dims[5], double dmin,
+                        double dstep, double smin, double sstep, void** device_ptr, int64_t* row_stride)
+{
+    GET_WMAP(wmap_id);
+    if (var < 0 || var >= BEATGPU_MAX_SLIPVARS) return fail(ctx, BEATGPU_E_ARG, "slip variable index %d", var);
+    if (store_dtype != BEATGPU_F32 && store_dtype != BEATGPU_F64) return fail(ctx, BEATGPU_E_ARG, "store dtype %d", store_dtype);
+    int rc = set_lib_meta(ctx, w, store_dtype, dims, dmin, dstep, smin, sstep);
+    if (rc) return rc;
+    if (w.G[var] && w.G_owned[var]) { cudaFree(w.G[var]); w.G[var] = nullptr; }
+    const size_t esz = store_dtype == BEATGPU_F32 ? 4 : 8;
+    const size_t rows = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
+    CK(cudaMalloc(&w.G[var], rows * w.ld * esz));
+    w.G_owned[var] = true;
+    if (device_ptr) *device_ptr = w.G[var];
+    if (row_stride) *row_stride = w.ld;
+    return BEATGPU_OK;
+}
+
+int beatgpu_upload_gflib(beatgpu_ctx* ctx, int wmap_id, int var, const void* traces, int src_dtype, int store_dtype,
+                         const int64_t dims[5], double dmin, double dstep, double smin, double sstep)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (!traces) return fail(ctx, BEATGPU_E_ARG, "upload_gflib: traces is NULL");
+    if (src_dtype != BEATGPU_F32 && src_dtype != BEATGPU_F64) return fail(ctx, BEATGPU_E_ARG, "source dtype %d", src_dtype);
+    void* dptr = nullptr;
+    int64_t ld = 0;
+    int rc = beatgpu_alloc_gflib(ctx, wmap_id, var, store_dtype, dims, dmin, dstep, smin, sstep, &dptr, &ld);
+    if (rc) return rc;
+    const int ns = (int)dims[4];
+    const size_t rows = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
+    const size_t ssz = src_dtype == BEATGPU_F32 ? 4 : 8, dsz = store_dtype == BEATGPU_F32 ? 4 : 8;
+    // stream in chunks of <= 256 MiB of source rows through a device staging buffer, repacking on the device
+    const size_t chunk_rows = std::max<size_t>(1, (256u << 20) / ((size_t)ns * ssz));
+    rc = ensure_tmp(ctx, 0, std::min(rows, chunk_rows) * ns * ssz);
+    if (rc) return rc;
+    for (size_t r0 = 0; r0 < rows; r0 += chunk_rows) {
+        const size_t nr = std::min(chunk_rows, rows - r0);
+        CK(cudaMemcpyAsync(ctx->d_tmp[0], (const char*)traces + r0 * ns * ssz, nr * ns * ssz, cudaMemcpyHostToDevice, ctx->stream));
+        char* dst = (char*)dptr + r0 * ld * dsz;
+        const int blocks = (int)std::min<size_t>(148 * 16, (nr * ld + 255) / 256);
+        if (src_dtype == BEATGPU_F64 && store_dtype == BEATGPU_F32)
+            repack_rows_kernel<double, float><<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->d_tmp[0], (float*)dst, (long)nr, ns, (long)ld);
+        else if (src_dtype == BEATGPU_F64 && store_dtype == BEATGPU_F64)
+            repack_rows_kernel<double, double><<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->d_tmp[0], (double*)dst, (long)nr, ns, (long)ld);
+        else if (src_dtype == BEATGPU_F32 && store_dtype == BEATGPU_F32)
+            repack_rows_kernel<float, float><<<blocks, 256, 0, ctx->stream>>>((const float*)ctx->d_tmp[0], (float*)dst, (long)nr, ns, (long)ld);
+        else
+            repack_rows_kernel<float, double><<<blocks, 256, 0, ctx->stream>>>((const float*)ctx->d_tmp[0], (double*)dst, (long)nr, ns, (long)ld);
+        CKL();
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return BEATGPU_OK;
+}
+
+int beatgpu_upload_data(beatgpu_ctx* ctx, int wmap_id, const double* data)
+{
+    GET_WMAP(wmap_id);
+    if (!data) return fail(ctx, BEATGPU_E_ARG, "upload_data: NULL");
+    return upload_vec(ctx, &w.d_data, data, (size_t)w.nt * w.ns);
+}
+
+int beatgpu_update_weights(beatgpu_ctx* ctx, int wmap_id, const double* U, const double* slog_pdet, double band_rtol)
+{
+    GET_WMAP(wmap_id);
+    if (!U || !slog_pdet) return fail(ctx, BEATGPU_E_ARG, "update_weights: NULL");
+    if (band_rtol < 0) band_rtol = 1e-13;
+    const int nt = w.nt, ns = w.ns;
+    // structure detection over all targets of the wavemap
+    bool lower = false;
+    int bw = 0;
+    for (int t = 0; t < nt; ++t) {
+        const double* Ut = U + (size_t)t * ns * ns;
+        double mx = 0.0;
+        for (size_t i = 0; i < (size_t)ns * ns; ++i) {
+            const double v = std::fabs(Ut[i]);
+            if (!(v == v)) return fail(ctx, BEATGPU_E_ARG, "update_weights: NaN in weight matrix of target %d", t);
+            mx = std::max(mx, v);
+        }
+        const double thr = band_rtol * mx;
+        for (int i = 0; i < ns; ++i) {
+            const double* row = Ut + (size_t)i * ns;
+            for (int j = 0; j < i && !lower; ++j) if (std::fabs(row[j]) > thr) lower = true;
+            for (int j = ns - 1; j > i + bw; --j) if (std::fabs(row[j]) > thr) { bw = j - i; break; }
+        }
+    }
+    int mode;
+    if (lower) mode = MISFIT_DENSE;
+    else if (bw == 0) mode = MISFIT_DIAG;
+    else if (bw <= 32 && bw + 1 < ns / 2) mode = MISFIT_BAND;
+    else mode = MISFIT_DENSE;
+    std::vector<double> W;
+    if (mode == MISFIT_DIAG) {
+        W.resize((size_t)nt * ns);
+        for (int t = 0; t < nt; ++t) for (int k = 0; k < ns; ++k) W[(size_t)t * ns + k] = U[(size_t)t * ns * ns + (size_t)k * ns + k];
+    } else if (mode == MISFIT_BAND) {
+        W.assign((size_t)nt * (bw + 1) * ns, 0.0);
+        for (int t = 0; t < nt; ++t)
+            for (int j = 0; j <= bw; ++j)
+                for (int k = 0; k + j < ns; ++k)
+                    W[((size_t)t * (bw + 1) + j) * ns + k] = U[(size_t)t * ns * ns + (size_t)k * ns + (k + j)];
+    } else {
+        W.resize((size_t)nt * ns * ns);
+        for (int t = 0; t < nt; ++t)
+            for (int k = 0; k < ns; ++k)
+                for (int j = 0; j < ns; ++j)
+                    W[(size_t)t * ns * ns + (size_t)j * ns + k] = U[(size_t)t * ns * ns + (size_t)k * ns + j];
+    }
+    // in-place update when the footprint is unchanged (between SMC stages): no reallocation
+    const size_t bytes = W.size() * sizeof(double);
+    if (w.d_W && w.W_bytes == bytes) {
+        CK(cudaMemcpyAsync(w.d_W, W.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        int rc = upload_vec(ctx, &w.d_W, W.data(), W.size());
+        if (rc) return rc;
+        w.W_bytes = bytes;
+    }
+    int rc = upload_vec(ctx, &w.d_slog_pdet, slog_pdet, nt);
+    if (rc) return rc;
+    w.misfit_mode = mode; w.bw = bw; w.dense_upper = lower ? 0 : 1;
+    return BEATGPU_OK;
+}
+
+int beatgpu_set_geodetic(beatgpu_ctx* ctx, int nobs, int nds, const int32_t* slo, const int32_t* shi, const double* const* G,
+                         const double* data, const double* odw, const double* U_concat, const double* slog_pdet,
+                         const int32_t* nsamples, const int32_t* hyper_idx)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (!ctx->layout_set) return fail(ctx, BEATGPU_E_NOTREADY, "set_geodetic: call set_fault and set_layout first");
+    if (nobs <= 0 || nds <= 0 || !slo || !shi || !G || !data || !odw || !U_concat || !slog_pdet || !nsamples || !hyper_idx)
+        return fail(ctx, BEATGPU_E_ARG, "set_geodetic: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    Geodetic& g = ctx->geo;
+    g.nobs = nobs; g.nds = nds;
+    g.lo.assign(slo, slo + nds); g.hi.assign(shi, shi + nds);
+    g.ut_ofs.resize(nds);
+    long tot = 0; int mx = 0;
+    for (int d = 0; d < nds; ++d) {
+        const int n = shi[d] - slo[d];
+        if (n <= 0 || slo[d] < 0 || shi[d] > nobs) return fail(ctx, BEATGPU_E_ARG, "set_geodetic: bad slice %d", d);
+        g.ut_ofs[d] = tot; tot += (long)n * n; mx = std::max(mx, n);
+    }
+    g.ut_total = tot; g.max_n = mx;
+    int rc;
+    for (int v = 0; v < ctx->layout.n_slipvars; ++v) {
+        if (!G[v]) return fail(ctx, BEATGPU_E_ARG, "set_geodetic: G[%d] is NULL", v);
+        if ((rc = upload_vec(ctx, &g.G[v], G[v], (size_t)ctx->np_total * nobs))) return rc;
+    }
+    if ((rc = upload_vec(ctx, &g.d_data, data, nobs))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_odw, odw, nobs))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_lo, g.lo.data(), nds))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_hi, g.hi.data(), nds))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_UT_ofs, g.ut_ofs.data(), nds))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_nsamp, nsamples, nds))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_hyper_idx, hyper_idx, nds))) return rc;
+    g.set = true;
+    assign_out_offsets(ctx);
+    return beatgpu_update_geodetic_weights(ctx, U_concat, slog_pdet);
+}
+
+int beatgpu_update_geodetic_weights(beatgpu_ctx* ctx, const double* U_concat, const double* slog_pdet)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    Geodetic& g = ctx->geo;
+    if (!g.set) return fail(ctx, BEATGPU_E_NOTREADY, "update_geodetic_weights: geodetic composite not set");
+    if (!U_concat || !slog_pdet) return fail(ctx, BEATGPU_E_ARG, "update_geodetic_weights: NULL");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<double> UT((size_t)g.ut_total);
+    std::vector<int> upper(g.nds, 1);
+    for (int d = 0; d < g.nds; ++d) {
+        const int n = g.hi[d] - g.lo[d];
+        const double* U = U_concat + g.ut_ofs[d];
+        double* T = UT.data() + g.ut_ofs[d];
+        for (int k = 0; k < n; ++k)
+            for (int j = 0; j < n; ++j) {
+                const double v = U[(size_t)k * n + j];
+                T[(size_t)j * n + k] = v;
+                if (j < k && v != 0.0) upper[d] = 0;
+            }
+    }
+    int rc;
+    if ((rc = upload_vec(ctx, &g.d_UT, UT.data(), UT.size()))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_upper, upper.data(), g.nds))) return rc;
+    if ((rc = upload_vec(ctx, &g.d_slog, slog_pdet, g.nds))) return rc;
+    return BEATGPU_OK;
+}
+
+int beatgpu_set_laplacian(beatgpu_ctx* ctx, const double* L, double sdet, int hyper_idx)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (!ctx->layout_set) return fail(ctx, BEATGPU_E_NOTREADY, "set_laplacian: call set_fault and set_layout first");
+    if (!L || hyper_idx < 0 || hyper_idx >= ctx->layout.n_hypers) return fail(ctx, BEATGPU_E_ARG, "set_laplacian: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int np = ctx->np_total;
+    std::vector<double> LT((size_t)np * np);
+    for (int i = 0; i < np; ++i) for (int j = 0; j < np; ++j) LT[(size_t)j * np + i] = L[(size_t)i * np + j];
+    int rc = upload_vec(ctx, &ctx->lap.d_LT, LT.data(), LT.size());
+    if (rc) return rc;
+    ctx->lap.sdet = sdet; ctx->lap.hyper_idx = hyper_idx; ctx->lap.set = true;
+    assign_out_offsets(ctx);
+    return BEATGPU_OK;
+}
+
+int beatgpu_n_outputs(beatgpu_ctx* ctx, int* n_out)
+{
+    if (!ctx || !n_out) return BEATGPU_E_ARG;
+    *n_out = n_outputs(ctx);
+    return BEATGPU_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int beatgpu_fast_sweep_batch(beatgpu_ctx* ctx, int sf, int B, const double* slowness, const int32_t* nuc_dip_idx,
+                             const int32_t* nuc_strike_idx, double* starttimes, int32_t* n_iter)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (!ctx->nsf) return fail(ctx, BEATGPU_E_NOTREADY, "fast_sweep_batch: call set_fault first");
+    if (sf < 0 || sf >= ctx->nsf || B <= 0 || !slowness || !nuc_dip_idx || !nuc_strike_idx || !starttimes)
+        return fail(ctx, BEATGPU_E_ARG, "fast_sweep_batch: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->h_nd[sf] * ctx->h_ns[sf];
+    // the reference wrapper raises on bad input rather than reading outside the grid
+    for (int b = 0; b < B; ++b)
+        if (nuc_dip_idx[b] < 0 || nuc_dip_idx[b] >= ctx->h_nd[sf] || nuc_strike_idx[b] < 0 || nuc_strike_idx[b] >= ctx->h_ns[sf])
+            return fail(ctx, BEATGPU_E_INDEX, "fast_sweep_batch: nucleation index (%d, %d) of chain %d outside the %dx%d grid",
+                        nuc_dip_idx[b], nuc_strike_idx[b], b, ctx->h_nd[sf], ctx->h_ns[sf]);
+    int rc;
+    const size_t nb = (size_t)B * n * sizeof(double);
+    if ((rc = ensure_tmp(ctx, 0, nb))) return rc;
+    if ((rc = ensure_tmp(ctx, 1, nb))) return rc;
+    if ((rc = ensure_tmp(ctx, 2, (size_t)B * 3 * sizeof(int)))) return rc;
+    int* d_idx = (int*)ctx->d_tmp[2];
+    CK(cudaMemcpyAsync(ctx->d_tmp[0], slowness, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_idx, nuc_dip_idx, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_idx + B, nuc_strike_idx, (size_t)B * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    SweepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n_dip = ctx->d_nd; a.n_strike = ctx->d_ns; a.patch_ofs = ctx->d_pofs; a.patch_size = ctx->d_psize;
+    a.n_subfaults = ctx->nsf; a.n_patches_total = ctx->np_total; a.max_np_sf = ctx->max_np_sf; a.B = B;
+    a.vel = (const double*)ctx->d_tmp[0]; a.vel_stride = n; a.is_slowness = 1;
+    a.nuc_dip_idx = d_idx; a.nuc_strike_idx = d_idx + B; a.only_sf = sf;
+    a.time = nullptr; a.t0 = (double*)ctx->d_tmp[1]; a.n_iter = n_iter ? d_idx + 2 * B : nullptr;
+    a.violations = ctx->d_viol; a.chain_bad = nullptr;
+    if ((rc = launch_sweep(ctx, a, B))) return rc;
+    CK(cudaMemcpyAsync(starttimes, ctx->d_tmp[1], nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_iter) CK(cudaMemcpyAsync(n_iter, d_idx + 2 * B, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BEATGPU_OK;
+}
+
+static int check_violations(beatgpu_ctx* ctx, const char* what)
+{
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, ctx->d_viol, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (v) {
+        CK(cudaMemsetAsync(ctx->d_viol, 0, sizeof(v), ctx->stream));
+        return fail(ctx, BEATGPU_E_INDEX, "%s: %llu GF-library / patch-grid indices out of range (affected outputs are NaN)", what, v);
+    }
+    return BEATGPU_OK;
+}
+
+int beatgpu_stack_batch(beatgpu_ctx* ctx, int wmap_id, int B, int nvar, const double* durations, const double* starttimes,
+                        const double* slips, double* synthetics)
+{
+    GET_WMAP(wmap_id);
+    if (B <= 0 || !durations || !starttimes || !slips || !synthetics) return fail(ctx, BEATGPU_E_ARG, "stack_batch: bad arguments");
+    int rc = check_lib(ctx, w, nvar);
+    if (rc) return rc;
+    const int np = (int)w.dims[1];
+    const size_t b_dur = (size_t)B * np * 8, b_st = (size_t)B * w.nt * np * 8, b_sl = (size_t)nvar * B * np * 8,
+                 b_out = (size_t)B * w.nt * w.ns * 8;
+    if ((rc = ensure_tmp(ctx, 0, b_dur)) || (rc = ensure_tmp(ctx, 1, b_st)) || (rc = ensure_tmp(ctx, 2, b_sl)) ||
+        (rc = ensure_tmp(ctx, 3, b_out)))
+        return rc;
+    CK(cudaMemcpyAsync(ctx->d_tmp[0], durations, b_dur, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tmp[1], starttimes, b_st, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tmp[2], slips, b_sl, cudaMemcpyHostToDevice, ctx->stream));
+    StackArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_static(w, a, nvar);
+    a.B = B;
+    a.dur = (const double*)ctx->d_tmp[0]; a.dur_sc = np;
+    for (int v = 0; v < nvar; ++v) { a.slip[v] = (const double*)ctx->d_tmp[2] + (size_t)v * B * np; a.slip_sc[v] = np; }
+    a.st = (const double*)ctx->d_tmp[1]; a.st_sc = (long)w.nt * np; a.st_st = np;
+    a.corr = nullptr; a.station_idx = nullptr;
+    a.synth = (double*)ctx->d_tmp[3];
+    a.violations = ctx->d_viol;
+    if ((rc = launch_stack<true>(ctx, w, a))) return rc;
+    CK(cudaMemcpyAsync(synthetics, ctx->d_tmp[3], b_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return check_violations(ctx, "stack_batch");
+}
+
+int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* residuals, const double* hypers, int n_hypers,
+                         double* logpts)
+{
+    GET_WMAP(wmap_id);
+    if (B <= 0 || !residuals || !hypers || n_hypers <= 0 || !logpts) return fail(ctx, BEATGPU_E_ARG, "misfit_batch: bad arguments");
+    if (w.misfit_mode < 0) return fail(ctx, BEATGPU_E_NOTREADY, "misfit_batch: weights not uploaded (update_weights)");
+    int rc;
+    const size_t b_r = (size_t)B * w.nt * w.ns * 8, b_h = (size_t)B * n_hypers * 8, b_o = (size_t)B * w.nt * 8;
+    if ((rc = ensure_tmp(ctx, 0, b_r)) || (rc = ensure_tmp(ctx, 1, b_h)) || (rc = ensure_tmp(ctx, 2, b_o))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_tmp[0], residuals, b_r, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tmp[1], hypers, b_h, cudaMemcpyHostToDevice, ctx->stream));
+    MisfitArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.nt = w.nt; a.ns = w.ns;
+    a.resid = (const double*)ctx->d_tmp[0];
+    a.hyp = (const double*)ctx->d_tmp[1]; a.hyp_sc = n_hypers; a.hyper_idx = w.d_hyper_idx;
+    a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
+    a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
+    a.logpts = (double*)ctx->d_tmp[2]; a.logpts_sc = w.nt; a.out_ofs = 0;
+    const size_t smem = (size_t)w.ns * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
+    CKL();
+    CK(cudaMemcpyAsync(logpts, ctx->d_tmp[2], b_o, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BEATGPU_OK;
+}
+
+// the fused path, everything on the device
+int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, double* logpts, double* like)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (B <= 0 || !q || !logpts) return fail(ctx, BEATGPU_E_ARG, "ffi_loglike_batch: bad arguments");
+    if (!ctx->layout_set) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: set_fault / set_layout not called");
+    if (ctx->wmaps.empty() && !ctx->geo.set && !ctx->lap.set) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: no composite configured");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_scratch(ctx, B))) return rc;
+    const beatgpu_layout& L = ctx->layout;
+    const int n_out = n_outputs(ctx);
+    for (auto& w : ctx->wmaps) {
+        if ((rc = check_lib(ctx, w, L.n_slipvars))) return rc;
+        if (!w.d_data) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: data of a wavemap not uploaded");
+        if (w.misfit_mode < 0) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: weights of a wavemap not uploaded");
+        if (w.has_station && !L.n_time_shifts) return fail(ctx, BEATGPU_E_ARG, "ffi_loglike_batch: wavemap has station corrections but the layout has no time_shifts");
+    }
+    VarRef hyp = var_ref(ctx, q, L.n_hypers ? L.off_hypers : -1, ctx->canon_hyp);
+
+    if (!ctx->wmaps.empty()) {
+        CK(cudaMemsetAsync(ctx->d_bad, 0, (size_t)B, ctx->stream));
+        // ---- rupture onset times for all chains / subfaults (seismic.py:1253-1272)
+        SweepArgs s;
+        memset(&s, 0, sizeof(s));
+        s.n_dip = ctx->d_nd; s.n_strike = ctx->d_ns; s.patch_ofs = ctx->d_pofs; s.patch_size = ctx->d_psize;
+        s.n_subfaults = ctx->nsf; s.n_patches_total = ctx->np_total; s.max_np_sf = ctx->max_np_sf; s.B = B;
+        VarRef vel = var_ref(ctx, q, L.off_velocities, ctx->canon_vel);
+        VarRef nd = var_ref(ctx, q, L.off_nucleation_dip, ctx->canon_ndip);
+        VarRef nst = var_ref(ctx, q, L.off_nucleation_strike, ctx->canon_nstr);
+        VarRef tm = var_ref(ctx, q, L.off_time, ctx->canon_time);
+        s.vel = vel.p; s.vel_stride = vel.stride; s.is_slowness = 0;
+        s.nuc_dip = nd.p; s.nuc_dip_stride = nd.stride; s.nuc_strike = nst.p; s.nuc_strike_stride = nst.stride;
+        s.nuc_dip_idx = nullptr; s.nuc_strike_idx = nullptr; s.only_sf = -1;
+        s.time = tm.p; s.time_stride = tm.stride;
+        s.t0 = ctx->d_t0; s.n_iter = nullptr; s.violations = ctx->d_viol; s.chain_bad = ctx->d_bad;
+        if ((rc = launch_sweep(ctx, s, B * ctx->nsf))) return rc;
+
+        // ---- per wavemap: gather + stack + residual + misfit (seismic.py:1275-1343)
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (auto& w : ctx->wmaps) {
+            StackArgs a;
+            memset(&a, 0, sizeof(a));
+            fill_static(w, a, L.n_slipvars);
+            a.B = B;
+            VarRef dur = var_ref(ctx, q, L.off_durations, ctx->canon_dur);
+            a.dur = dur.p; a.dur_sc = dur.stride;
+            for (int v = 0; v < L.n_slipvars; ++v) {
+                VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
+                a.slip[v] = sl.p; a.slip_sc[v] = sl.stride;
+            }
+            a.st = ctx->d_t0; a.st_sc = ctx->np_total; a.st_st = 0;
+            if (w.has_station) {
+                VarRef ts = var_ref(ctx, q, L.off_time_shifts, ctx->canon_ts);
+                a.corr = ts.p; a.corr_sc = ts.stride;
+            } else {
+                a.corr = nullptr; a.station_idx = nullptr;
+            }
+            a.hyp = hyp.p; a.hyp_sc = hyp.stride;
+            a.logpts = logpts; a.logpts_sc = n_out; a.out_ofs = w.out_ofs;
+            a.synth = nullptr; a.chain_bad = ctx->d_bad; a.violations = ctx->d_viol;
+            if ((rc = launch_stack<false>(ctx, w, a))) return rc;
+        }
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        ctx->ev_valid = true;
+    }
+
+    if (ctx->geo.set) {
+        Geodetic& g = ctx->geo;
+        GeoArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = B; a.np = ctx->np_total; a.nobs = g.nobs; a.ndatasets = g.nds; a.nvar = L.n_slipvars;
+        for (int v = 0; v < L.n_slipvars; ++v) {
+            a.G[v] = g.G[v];
+            VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
+            a.slip[v] = sl.p; a.slip_sc[v] = sl.stride;
+        }
+        a.data = g.d_data; a.odw = g.d_odw; a.lo = g.d_lo; a.hi = g.d_hi; a.UT = g.d_UT; a.UT_ofs = g.d_UT_ofs;
+        a.upper = g.d_upper; a.slog_pdet = g.d_slog; a.nsamp = g.d_nsamp; a.hyper_idx = g.d_hyper_idx;
+        a.hyp = hyp.p; a.hyp_sc = hyp.stride;
+        a.logpts = logpts; a.logpts_sc = n_out; a.out_ofs = g.out_ofs; a.max_n = g.max_n;
+        const size_t smem = ((size_t)L.n_slipvars * ctx->np_total + g.max_n) * sizeof(double);
+        if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) return fail(ctx, BEATGPU_E_ARG, "geodetic dataset too large for shared memory (%zu B)", smem);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(geodetic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        geodetic_kernel<<<(unsigned)((long)g.nds * B), 256, smem, ctx->stream>>>(a);
+        CKL();
+    }
+
+    if (ctx->lap.set) {
+        LapArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = B; a.np = ctx->np_total; a.nvar = L.n_slipvars;
+        a.LT = ctx->lap.d_LT; a.sdet = ctx->lap.sdet; a.hyper_idx = ctx->lap.hyper_idx;
+        for (int v = 0; v < L.n_slipvars; ++v) {
+            VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
+            a.slip[v] = sl.p; a.slip_sc[v] = sl.stride;
+        }
+        a.hyp = hyp.p; a.hyp_sc = hyp.stride;
+        a.logpts = logpts; a.logpts_sc = n_out; a.out_ofs = ctx->lap.out_ofs;
+        laplacian_kernel<<<B, 256, (size_t)ctx->np_total * sizeof(double), ctx->stream>>>(a);
+        CKL();
+    }
+
+    if (like) {
+        sum_like_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(logpts, like, B, n_out);
+        CKL();
+    }
+    return BEATGPU_OK;
+}
+
+int beatgpu_ffi_loglike_batch(beatgpu_ctx* ctx, int B, const double* q, double* logpts, double* like)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (B <= 0 || !q || !logpts) return fail(ctx, BEATGPU_E_ARG, "ffi_loglike_batch: bad arguments");
+    if (!ctx->layout_set) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: set_fault / set_layout not called");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure_scratch(ctx, B))) return rc;
+    const int n_out = n_outputs(ctx);
+    CK(cudaMemcpyAsync(ctx->d_q, q, (size_t)B * ctx->layout.n_params * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = beatgpu_ffi_loglike_batch_dev(ctx, B, ctx->d_q, ctx->d_logpts, ctx->d_like))) return rc;
+    CK(cudaMemcpyAsync(logpts, ctx->d_logpts, (size_t)B * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (like) CK(cudaMemcpyAsync(like, ctx->d_like, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_violations(ctx, "ffi_loglike_batch");
+}
+
+int beatgpu_get_starttimes(beatgpu_ctx* ctx, int B, double* starttimes)
+{
+    if (!ctx || !starttimes) return BEATGPU_E_ARG;
+    if (B <= 0 || B > ctx->cap_B || !ctx->d_t0) return fail(ctx, BEATGPU_E_NOTREADY, "get_starttimes: no evaluation of >= %d chains yet", B);
+    CK(cudaMemcpyAsync(starttimes, ctx->d_t0, (size_t)B * ctx->np_total * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return BEATGPU_OK;
+}
+
+int beatgpu_index_violations(beatgpu_ctx* ctx, int64_t* count)
+{
+    if (!ctx || !count) return BEATGPU_E_ARG;
+    unsigned long long v = 0;
+    CK(cudaMemcpyAsync(&v, ctx->d_viol, sizeof(v), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_viol, 0, sizeof(v), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *count = (int64_t)v;
+    return BEATGPU_OK;
+}
+
+int beatgpu_launch_count(beatgpu_ctx* ctx, int64_t* n)
+{
+    if (!ctx || !n) return BEATGPU_E_ARG;
+    *n = ctx->n_launches;
+    return BEATGPU_OK;
+}
+
+int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms) return BEATGPU_E_ARG;
+    if (!ctx->ev_valid) return fail(ctx, BEATGPU_E_NOTREADY, "last_stack_ms: no fused evaluation yet");
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return BEATGPU_OK;
+}
+
+}  // extern "C"

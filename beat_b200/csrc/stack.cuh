@@ -1,0 +1,347 @@
+// stack.cuh -- the roofline kernel: fused GF-library gather + slip-weighted stack over patches
+//              + residual + covariance-weighted misfit, one CTA per (chain, target).
+//
+// Replaces, for B chains at once, the sub-graph the reference builds in
+// SeismicDistributerComposite.get_formula (beat/models/seismic.py:1283-1341):
+//   starttimes[t,p] = t0[p] - corr[station(t)]                          (:1283-1296)
+//   synth[t,:]     += SeismicGFLibrary.stack_all(...) for every slip var (:1317-1330; beat/ffi/base.py:607-709,
+//                     index mapping :486-521,:535-568)
+//   residual        = data - synth                                       (:1332)
+//   logpts[t]       = multivariate_normal_chol(...)                      (:1335-1341; beat/models/distributions.py:119-138)
+//
+// Data layout in HBM: library G_var is (ntargets, npatches, ndurations, nstarttimes, ld) with ld = nsamples rounded
+// up to a 16-byte multiple, float32 or float64.  One "row" = the ld contiguous samples of one (t, p, d, s) entry;
+// the kernel only ever reads whole rows, 16 bytes per lane (one LDG.128 per lane per row for f32 with ns <= 128).
+//
+// Work decomposition: grid = nt * B CTAs, target-major (blockIdx = t*B + c), so CTAs resident at the same time
+// work on the same target and march through its patches in near lock-step: rows of one (t, p) block
+// (ndur*nst rows, ~0.5 MB) requested by different chains are served from the 126 MB L2 instead of HBM.
+// Inside the CTA: (1) all threads build a per-patch "plan" in shared memory (row indices + f64 weights of the
+// K taps x nvar slip components; every index/weight is computed in f64 exactly as the reference does);
+// (2) each warp streams its share of patches, all K*nvar row loads of two patches in flight per lane, and
+// accumulates in f64 registers; (3) cross-warp reduction, residual against the data row, (4) misfit epilogue:
+// z = U r with U diagonal / upper-banded / dense, quad = z.z via warp shuffles, logpt written per (chain, dataset).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace beatgpu {
+
+constexpr int kStackThreads = 128;
+constexpr int kStackWarps = kStackThreads / 32;
+constexpr int kPlanChunk = 256;          // patches planned per pass (bounds shared memory for any npatches)
+constexpr int kWindow = 128;             // samples per pass (one 16-byte vector per lane for f32)
+
+enum MisfitMode { MISFIT_DIAG = 0, MISFIT_BAND = 1, MISFIT_DENSE = 2 };
+
+struct StackArgs {
+    // library
+    const void* G[BEATGPU_MAX_SLIPVARS];
+    int nvar;
+    int nt, np, ndur, nst, ns;
+    long ld;                              // row stride in elements
+    double dur_min, dur_step, st_min, st_step;
+    int B;
+    // per-chain inputs (pointer + stride in doubles between chains; stride 0 = shared by all chains)
+    const double* dur;  long dur_sc;                                     // [np]
+    const double* slip[BEATGPU_MAX_SLIPVARS]; long slip_sc[BEATGPU_MAX_SLIPVARS];   // [np]
+    const double* st;   long st_sc; long st_st;                          // start times [np] per chain (st_st: stride between targets, 0 in fused mode)
+    const double* corr; long corr_sc;                                    // time_shifts [n_time_shifts] or nullptr
+    const int* station_idx;                                              // [nt] or nullptr
+    const double* hyp;  long hyp_sc;                                     // hypers [n_hypers]
+    const int* hyper_idx;                                                // [nt]
+    // static per-target operands
+    const double* data;                   // [nt, ns]
+    int misfit_mode; int bw; int dense_upper;
+    const double* W;                      // DIAG: [nt, ns]; BAND: [nt, bw+1, ns] (W[t][j][k] = U[k][k+j]); DENSE: [nt, ns, ns] transposed (W[t][j][k] = U[k][j])
+    const double* slog_pdet;              // [nt]
+    const int* nsamp;                     // [nt]  (M)
+    // outputs
+    double* logpts; long logpts_sc; int out_ofs;     // logpts[c*logpts_sc + out_ofs + t]
+    double* synth;                        // optional [B, nt, ns]
+    const unsigned char* chain_bad;       // optional [B]
+    unsigned long long* violations;
+};
+
+template <int K, int NVAR>
+struct __align__(16) PatchPlan {
+    int row[4];                // library row index of each tap (already moved onto a valid row when its weight is zero)
+    double w[K * NVAR];        // weight of tap k, slip variable v at w[v*K + k]
+};
+
+// sample index (within the window) of element e (0..3) held by vector slot j
+template <typename T> __device__ __forceinline__ int slot_sample(int j, int e);
+template <> __device__ __forceinline__ int slot_sample<float>(int j, int e) { return 4 * j + e; }
+// f64 rows are read as two 16-byte vectors per lane: vector j covers samples 2j,2j+1 and vector j+32 covers 64+2j,64+2j+1
+template <> __device__ __forceinline__ int slot_sample<double>(int j, int e) { return (e < 2) ? (2 * j + e) : (64 + 2 * j + (e - 2)); }
+
+template <typename T, int K, int NVAR, bool WRITE_SYNTH>
+__global__ void __launch_bounds__(kStackThreads)
+gf_stack_misfit_kernel(StackArgs a)
+{
+    using Plan = PatchPlan<K, NVAR>;
+    __shared__ Plan plan[kPlanChunk];
+    __shared__ double red[kStackWarps][kWindow];
+    __shared__ double red_q[kStackWarps];
+    __shared__ int s_bad;
+    extern __shared__ double resid[];            // [ns] residual (or synth) of this (chain, target)
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int c = blockIdx.x % a.B;
+    const int t = blockIdx.x / a.B;
+
+    if (tid == 0) s_bad = (a.chain_bad && a.chain_bad[c]) ? 1 : 0;
+
+    const double* dur = a.dur + (long)c * a.dur_sc;
+    const double* st = a.st + (long)c * a.st_sc + (long)t * a.st_st;
+    double corr = 0.0;
+    if (a.corr) corr = a.corr[(long)c * a.corr_sc + a.station_idx[t]];
+    const long rows_per_patch = (long)a.ndur * a.nst;
+
+    for (int s0 = 0; s0 < a.ns; s0 += kWindow) {
+        const int wlen = min(kWindow, a.ns - s0);
+        const int nvec = (wlen * (int)sizeof(T) + 15) / 16;      // 16-byte vectors in this window of a row
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+
+        for (int p0 = 0; p0 < a.np; p0 += kPlanChunk) {
+            const int pn = min(kPlanChunk, a.np - p0);
+            __syncthreads();                                     // previous chunk fully consumed
+            // ---------------- (1) plan: indices + weights, f64, reference arithmetic ----------------
+            for (int i = tid; i < pn; i += kStackThreads) {
+                const int p = p0 + i;
+                const double x = (dur[p] - a.dur_min) / a.dur_step;                       // base.py:556 / :561
+                const double y = ((st[p] - corr) - a.st_min) / a.st_step;                 // seismic.py:1283-1291, base.py:509 / :514
+                const long base = ((long)t * a.np + p) * rows_per_patch;
+                Plan pl;
+                bool viol = false;
+                if (K == 1) {                                                            // nearest neighbour (base.py:506-512,553-559)
+                    const int di = (int)rint(x);          // round-half-even; the int16 cast of the reference cannot matter in range
+                    const int si = (int)rint(y);
+                    viol = (x != x) || (y != y) || (di < 0) || (di >= a.ndur) || (si < 0) || (si >= a.nst);
+                    pl.row[0] = viol ? 0 : (int)(base + (long)di * a.nst + si);
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v) pl.w[v] = a.slip[v][(long)c * a.slip_sc[v] + p];
+                } else {                                                                 // multilinear (base.py:513-517,560-564,662-679)
+                    const int dc = (int)ceil(x);
+                    const int sc = (int)ceil(y);
+                    const double rf = (double)dc - x;
+                    const double sf = (double)sc - y;
+                    // a "floor" tap has weight exactly 0 when the coordinate is integral; numpy then reads a wrapped
+                    // (valid) row and multiplies by 0 -- we read the ceil row instead.  Any tap with non-zero weight
+                    // outside the library is a violation.
+                    const int dfl = (rf == 0.0) ? dc : dc - 1;
+                    const int sfl = (sf == 0.0) ? sc : sc - 1;
+                    viol = (x != x) || (y != y) || (dc < 0) || (dc >= a.ndur) || (dfl < 0) || (sc < 0) || (sc >= a.nst) || (sfl < 0);
+                    if (viol) {
+                        pl.row[0] = pl.row[1] = pl.row[2] = pl.row[3] = 0;
+                    } else {
+                        pl.row[0] = (int)(base + (long)dc * a.nst + sc);      // st ceil,  rt ceil
+                        pl.row[1] = (int)(base + (long)dc * a.nst + sfl);     // st floor, rt ceil
+                        pl.row[2] = (int)(base + (long)dfl * a.nst + sc);     // st ceil,  rt floor
+                        pl.row[3] = (int)(base + (long)dfl * a.nst + sfl);    // st floor, rt floor
+                    }
+                    const double w_cc = (1.0 - sf) * (1.0 - rf);
+                    const double w_fc = sf * (1.0 - rf);
+                    const double w_cf = (1.0 - sf) * rf;
+                    const double w_ff = sf * rf;
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v) {
+                        const double u = a.slip[v][(long)c * a.slip_sc[v] + p];
+                        pl.w[v * K + 0] = w_cc * u;
+                        pl.w[v * K + 1] = w_fc * u;
+                        pl.w[v * K + 2] = w_cf * u;
+                        pl.w[v * K + 3] = w_ff * u;
+                    }
+                }
+                if (viol) {
+                    if (s0 == 0) atomicAdd(a.violations, 1ULL);
+                    s_bad = 1;
+#pragma unroll
+                    for (int q = 0; q < K * NVAR; ++q) pl.w[q] = 0.0;
+                }
+                plan[i] = pl;
+            }
+            __syncthreads();
+
+            // ---------------- (2) stream rows: K*NVAR rows per patch, two patches in flight ----------------
+            if (sizeof(T) == 4) {
+                const bool active = lane < nvec;
+                for (int i = warp; i < pn; i += 2 * kStackWarps) {
+                    const int i2 = i + kStackWarps;
+                    const bool has2 = i2 < pn;
+                    float4 g[2][K * NVAR];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int ii = (u == 0) ? i : (has2 ? i2 : i);
+                        const bool ld_on = active && (u == 0 || has2);
+#pragma unroll
+                        for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+                            for (int k = 0; k < K; ++k) {
+                                const float* row = reinterpret_cast<const float*>(a.G[v]) + (long)plan[ii].row[k] * a.ld + s0;
+                                g[u][v * K + k] = ld_on ? __ldg(reinterpret_cast<const float4*>(row) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (u == 1 && !has2) break;
+                        const int ii = (u == 0) ? i : i2;
+#pragma unroll
+                        for (int q = 0; q < K * NVAR; ++q) {
+                            const double w = plan[ii].w[q];
+                            acc[0] = fma(w, (double)g[u][q].x, acc[0]);
+                            acc[1] = fma(w, (double)g[u][q].y, acc[1]);
+                            acc[2] = fma(w, (double)g[u][q].z, acc[2]);
+                            acc[3] = fma(w, (double)g[u][q].w, acc[3]);
+                        }
+                    }
+                }
+            } else {
+                // f64 storage: a window of 128 samples = 64 16-byte vectors; lane reads vectors `lane` and `lane+32`
+                const bool act0 = lane < nvec, act1 = (lane + 32) < nvec;
+                for (int i = warp; i < pn; i += kStackWarps) {
+                    double2 g0[K * NVAR], g1[K * NVAR];
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const double* row = reinterpret_cast<const double*>(a.G[v]) + (long)plan[i].row[k] * a.ld + s0;
+                            g0[v * K + k] = act0 ? __ldg(reinterpret_cast<const double2*>(row) + lane) : make_double2(0.0, 0.0);
+                            g1[v * K + k] = act1 ? __ldg(reinterpret_cast<const double2*>(row) + lane + 32) : make_double2(0.0, 0.0);
+                        }
+#pragma unroll
+                    for (int q = 0; q < K * NVAR; ++q) {
+                        const double w = plan[i].w[q];
+                        acc[0] = fma(w, g0[q].x, acc[0]);
+                        acc[1] = fma(w, g0[q].y, acc[1]);
+                        acc[2] = fma(w, g1[q].x, acc[2]);
+                        acc[3] = fma(w, g1[q].y, acc[3]);
+                    }
+                }
+            }
+        }
+
+        // ---------------- (3) cross-warp reduction of this window, residual ----------------
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int sidx = slot_sample<T>(lane, e);
+            if (sidx < kWindow) red[warp][sidx] = acc[e];
+        }
+        __syncthreads();
+        for (int k = tid; k < wlen; k += kStackThreads) {
+            double s = red[0][k];
+#pragma unroll
+            for (int w = 1; w < kStackWarps; ++w) s += red[w][k];
+            if (WRITE_SYNTH) {
+                a.synth[((long)c * a.nt + t) * a.ns + s0 + k] = s;
+            } else {
+                resid[s0 + k] = a.data[(long)t * a.ns + s0 + k] - s;                     // seismic.py:1332
+            }
+        }
+        __syncthreads();
+    }
+
+    if (WRITE_SYNTH) {
+        if (s_bad) for (int k = tid; k < a.ns; k += kStackThreads) a.synth[((long)c * a.nt + t) * a.ns + k] = CUDART_NAN;
+        return;
+    }
+
+    // ---------------- (4) misfit: quad = |U r|^2  (distributions.py:128,136) ----------------
+    double q = 0.0;
+    const int ns = a.ns;
+    if (a.misfit_mode == MISFIT_DIAG) {
+        const double* Wt = a.W + (long)t * ns;
+        for (int k = tid; k < ns; k += kStackThreads) { const double z = Wt[k] * resid[k]; q = fma(z, z, q); }
+    } else if (a.misfit_mode == MISFIT_BAND) {
+        const double* Wt = a.W + (long)t * (a.bw + 1) * ns;
+        for (int k = tid; k < ns; k += kStackThreads) {
+            double z = 0.0;
+            const int jmax = min(a.bw, ns - 1 - k);
+            for (int j = 0; j <= jmax; ++j) z = fma(Wt[(long)j * ns + k], resid[k + j], z);
+            q = fma(z, z, q);
+        }
+    } else {
+        const double* Wt = a.W + (long)t * ns * ns;
+        for (int k = tid; k < ns; k += kStackThreads) {
+            double z = 0.0;
+            for (int j = a.dense_upper ? k : 0; j < ns; ++j) z = fma(Wt[(long)j * ns + k], resid[j], z);
+            q = fma(z, z, q);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) red_q[warp] = q;
+    __syncthreads();
+    if (tid == 0) {
+        double quad = red_q[0];
+#pragma unroll
+        for (int w = 1; w < kStackWarps; ++w) quad += red_q[w];
+        const double hp = a.hyp[(long)c * a.hyp_sc + a.hyper_idx[t]];
+        const double M = (double)(short)a.nsamp[t];                                       // tt.cast(..., "int16") distributions.py:120
+        const double norm = M * (2.0 * hp + 1.8378770664093453);                          // log(2*pi), distributions.py:13,129
+        double lp = (-0.5) * (a.slog_pdet[t] + norm + (1.0 / exp(hp * 2.0)) * quad);      // distributions.py:132-137
+        if (s_bad) lp = CUDART_NAN;
+        a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = lp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// standalone multivariate_normal_chol over residuals [B, nt, ns] (beat/models/distributions.py:72-140)
+// ---------------------------------------------------------------------------------------------------------
+struct MisfitArgs {
+    int B, nt, ns;
+    const double* resid;                  // [B, nt, ns]
+    const double* hyp; long hyp_sc; const int* hyper_idx;
+    int misfit_mode; int bw; int dense_upper;
+    const double* W; const double* slog_pdet; const int* nsamp;
+    double* logpts; long logpts_sc; int out_ofs;
+};
+
+__global__ void __launch_bounds__(kStackThreads) misfit_kernel(MisfitArgs a)
+{
+    extern __shared__ double resid[];
+    __shared__ double red_q[kStackWarps];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = blockIdx.x % a.B, t = blockIdx.x / a.B;
+    const int ns = a.ns;
+    const double* r = a.resid + ((long)c * a.nt + t) * ns;
+    for (int k = tid; k < ns; k += kStackThreads) resid[k] = r[k];
+    __syncthreads();
+    double q = 0.0;
+    if (a.misfit_mode == MISFIT_DIAG) {
+        const double* Wt = a.W + (long)t * ns;
+        for (int k = tid; k < ns; k += kStackThreads) { const double z = Wt[k] * resid[k]; q = fma(z, z, q); }
+    } else if (a.misfit_mode == MISFIT_BAND) {
+        const double* Wt = a.W + (long)t * (a.bw + 1) * ns;
+        for (int k = tid; k < ns; k += kStackThreads) {
+            double z = 0.0;
+            const int jmax = min(a.bw, ns - 1 - k);
+            for (int j = 0; j <= jmax; ++j) z = fma(Wt[(long)j * ns + k], resid[k + j], z);
+            q = fma(z, z, q);
+        }
+    } else {
+        const double* Wt = a.W + (long)t * ns * ns;
+        for (int k = tid; k < ns; k += kStackThreads) {
+            double z = 0.0;
+            for (int j = a.dense_upper ? k : 0; j < ns; ++j) z = fma(Wt[(long)j * ns + k], resid[j], z);
+            q = fma(z, z, q);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) red_q[warp] = q;
+    __syncthreads();
+    if (tid == 0) {
+        double quad = red_q[0];
+        for (int w = 1; w < kStackWarps; ++w) quad += red_q[w];
+        const double hp = a.hyp[(long)c * a.hyp_sc + a.hyper_idx[t]];
+        const double M = (double)(short)a.nsamp[t];
+        const double norm = M * (2.0 * hp + 1.8378770664093453);
+        a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = (-0.5) * (a.slog_pdet[t] + norm + (1.0 / exp(hp * 2.0)) * quad);
+    }
+}
+
+}  // namespace beatgpu

@@ -1,0 +1,322 @@
+"""
+ctypes binding of ``libbeatgpu.so`` (C-ABI declared in ``include/beatgpu.h``).
+
+This is the only place Python touches the native library.  There is NO CPU fallback: if the shared
+object is missing or cannot be loaded, importing a GPU code path raises ``BeatGpuLibraryError`` with the
+build command; if no CUDA device is present, ``Context()`` raises ``BeatGpuError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbeatgpu.so")
+
+F32, F64 = 0, 1
+NEAREST, MULTILINEAR = 0, 1
+INTERPOLATION = {"nearest_neighbor": NEAREST, "multilinear": MULTILINEAR}
+MAX_SLIPVARS = 3
+
+E_CUDA, E_ARG, E_INDEX, E_NOTREADY, E_NONFINITE = 1, 2, 3, 4, 5
+
+
+class BeatGpuLibraryError(ImportError):
+    pass
+
+
+class BeatGpuError(RuntimeError):
+    """CUDA / call-order failure reported by libbeatgpu."""
+
+    def __init__(self, code, msg):
+        super().__init__("libbeatgpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+class GFLibraryError(Exception):
+    """Same name as the reference's error type (beat/ffi/base.py:58-59)."""
+
+
+class Layout(C.Structure):
+    _fields_ = [
+        ("n_params", C.c_int32),
+        ("n_slipvars", C.c_int32),
+        ("off_slip", C.c_int32 * MAX_SLIPVARS),
+        ("off_durations", C.c_int32),
+        ("off_velocities", C.c_int32),
+        ("off_nucleation_strike", C.c_int32),
+        ("off_nucleation_dip", C.c_int32),
+        ("off_time", C.c_int32),
+        ("off_hypers", C.c_int32),
+        ("n_hypers", C.c_int32),
+        ("off_time_shifts", C.c_int32),
+        ("n_time_shifts", C.c_int32),
+    ]
+
+
+# every symbol include/beatgpu.h declares, with its ctypes signature (tests check the .so exports them all)
+_P = C.c_void_p
+_SIGNATURES = {
+    "beatgpu_version": (C.c_int, []),
+    "beatgpu_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "beatgpu_ctx_destroy": (None, [_P]),
+    "beatgpu_last_error": (C.c_char_p, [_P]),
+    "beatgpu_sync": (C.c_int, [_P]),
+    "beatgpu_set_stream": (C.c_int, [_P, _P]),
+    "beatgpu_device_info": (C.c_int, [_P, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
+    "beatgpu_set_fault": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "beatgpu_set_layout": (C.c_int, [_P, C.POINTER(Layout), _P]),
+    "beatgpu_add_wavemap": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]),
+    "beatgpu_upload_gflib": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_double, C.c_double,
+                                       C.c_double, C.c_double]),
+    "beatgpu_alloc_gflib": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, C.c_double, C.c_double, C.c_double,
+                                      C.c_double, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "beatgpu_upload_data": (C.c_int, [_P, C.c_int, _P]),
+    "beatgpu_update_weights": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
+    "beatgpu_set_geodetic": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "beatgpu_update_geodetic_weights": (C.c_int, [_P, _P, _P]),
+    "beatgpu_set_laplacian": (C.c_int, [_P, _P, C.c_double, C.c_int]),
+    "beatgpu_n_outputs": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "beatgpu_fast_sweep_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "beatgpu_stack_batch": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "beatgpu_misfit_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "beatgpu_ffi_loglike_batch": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "beatgpu_ffi_loglike_batch_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "beatgpu_get_starttimes": (C.c_int, [_P, C.c_int, _P]),
+    "beatgpu_index_violations": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "beatgpu_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "beatgpu_last_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libbeatgpu.so (once).  Raises BeatGpuLibraryError if it is not built -- never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BeatGpuLibraryError(
+                "%s not found.  Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc -gencode arch=compute_100a,code=sm_100a).  beat_b200 has no CPU fallback." % LIB_PATH)
+        try:
+            lib = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise BeatGpuLibraryError("cannot load %s: %s" % (LIB_PATH, e))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), a.shape))
+    return a
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One libbeatgpu context = one (process, GPU).  Thin, typed wrappers over the C entry points."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        h = C.c_void_p()
+        rc = self._lib.beatgpu_ctx_create(int(device), C.byref(h))
+        if rc:
+            raise BeatGpuError(rc, self._lib.beatgpu_last_error(None).decode())
+        self._h = h
+        self.device = int(device)
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.beatgpu_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            msg = self._lib.beatgpu_last_error(self._h).decode()
+            if rc == E_INDEX:
+                raise IndexError(msg)            # what numpy/pytensor raise in the reference
+            if rc == E_ARG:
+                raise ValueError(msg)
+            raise BeatGpuError(rc, msg)
+
+    # ------------------------------------------------------------------ context
+    def sync(self):
+        self._check(self._lib.beatgpu_sync(self._h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.beatgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def device_info(self):
+        n = C.c_int()
+        buf = C.create_string_buffer(256)
+        self._check(self._lib.beatgpu_device_info(self._h, C.byref(n), buf, 256))
+        return n.value, buf.value.decode()
+
+    # ------------------------------------------------------------------ operands
+    def set_fault(self, n_patch_dip, n_patch_strike, patch_size):
+        nd, ns, ps = _i32(n_patch_dip), _i32(n_patch_strike), _f64(patch_size)
+        self._check(self._lib.beatgpu_set_fault(self._h, len(nd), _ptr(nd), _ptr(ns), _ptr(ps)))
+
+    def set_layout(self, layout: Layout, fixed=None):
+        fx = None if fixed is None else _f64(fixed)
+        self._check(self._lib.beatgpu_set_layout(self._h, C.byref(layout), _ptr(fx)))
+
+    def add_wavemap(self, n_targets, n_samples, interpolation, station_idx, hyper_idx, nsamples):
+        st = None if station_idx is None else _i32(station_idx)
+        hi, nsm = _i32(hyper_idx), _i32(nsamples)
+        wid = C.c_int()
+        self._check(self._lib.beatgpu_add_wavemap(self._h, int(n_targets), int(n_samples),
+                                                  INTERPOLATION.get(interpolation, interpolation),
+                                                  _ptr(st), _ptr(hi), _ptr(nsm), C.byref(wid)))
+        return wid.value
+
+    def upload_gflib(self, wmap, slipvar, traces, store_dtype, dur_min, dur_step, st_min, st_step):
+        if traces.dtype == np.float64:
+            src = F64
+        elif traces.dtype == np.float32:
+            src = F32
+        else:
+            raise GFLibraryError("GF library dtype %s not supported" % traces.dtype)
+        if traces.ndim != 5 or not traces.flags["C_CONTIGUOUS"]:
+            raise GFLibraryError("GF library must be a C-contiguous 5-d array (targets, patches, durations, starttimes, samples)")
+        dims = np.asarray(traces.shape, dtype=np.int64)
+        self._check(self._lib.beatgpu_upload_gflib(self._h, wmap, slipvar, traces.ctypes.data_as(C.c_void_p), src,
+                                                   store_dtype, _ptr(dims), dur_min, dur_step, st_min, st_step))
+
+    def alloc_gflib(self, wmap, slipvar, store_dtype, dims, dur_min, dur_step, st_min, st_step):
+        dims = np.asarray(dims, dtype=np.int64)
+        p, ld = C.c_void_p(), C.c_int64()
+        self._check(self._lib.beatgpu_alloc_gflib(self._h, wmap, slipvar, store_dtype, _ptr(dims), dur_min, dur_step,
+                                                  st_min, st_step, C.byref(p), C.byref(ld)))
+        return p.value, ld.value
+
+    def upload_data(self, wmap, data):
+        d = _f64(data)
+        self._check(self._lib.beatgpu_upload_data(self._h, wmap, _ptr(d)))
+
+    def update_weights(self, wmap, U, slog_pdet, band_rtol=-1.0):
+        U, lp = _f64(U), _f64(slog_pdet)
+        self._check(self._lib.beatgpu_update_weights(self._h, wmap, _ptr(U), _ptr(lp), band_rtol))
+
+    def set_geodetic(self, slices, G_list, data, odw, U_list, slog_pdet, nsamples, hyper_idx):
+        lo = _i32([s[0] for s in slices])
+        hi = _i32([s[1] for s in slices])
+        Gs = [_f64(g) for g in G_list]
+        arr = (C.c_void_p * len(Gs))(*[g.ctypes.data for g in Gs])
+        data, odw = _f64(data), _f64(odw)
+        Ucat = np.concatenate([_f64(u).ravel() for u in U_list])
+        lp, nsm, hix = _f64(slog_pdet), _i32(nsamples), _i32(hyper_idx)
+        self._check(self._lib.beatgpu_set_geodetic(self._h, len(data), len(slices), _ptr(lo), _ptr(hi),
+                                                   C.cast(arr, C.c_void_p), _ptr(data), _ptr(odw), _ptr(Ucat), _ptr(lp),
+                                                   _ptr(nsm), _ptr(hix)))
+
+    def update_geodetic_weights(self, U_list, slog_pdet):
+        Ucat = np.concatenate([_f64(u).ravel() for u in U_list])
+        lp = _f64(slog_pdet)
+        self._check(self._lib.beatgpu_update_geodetic_weights(self._h, _ptr(Ucat), _ptr(lp)))
+
+    def set_laplacian(self, L, sdet, hyper_idx):
+        L = _f64(L)
+        self._check(self._lib.beatgpu_set_laplacian(self._h, _ptr(L), float(sdet), int(hyper_idx)))
+
+    def n_outputs(self):
+        n = C.c_int()
+        self._check(self._lib.beatgpu_n_outputs(self._h, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------ hot path
+    def fast_sweep_batch(self, subfault, slowness, nuc_dip_idx, nuc_strike_idx, return_iters=False):
+        s = _f64(slowness)
+        if s.ndim != 2:
+            raise ValueError("slowness must be [B, npatches_subfault]")
+        B = s.shape[0]
+        di, si = _i32(nuc_dip_idx), _i32(nuc_strike_idx)
+        if di.shape != (B,) or si.shape != (B,):
+            raise ValueError("nucleation indices must be [B]")
+        out = np.empty_like(s)
+        it = np.zeros(B, dtype=np.int32) if return_iters else None
+        self._check(self._lib.beatgpu_fast_sweep_batch(self._h, subfault, B, _ptr(s), _ptr(di), _ptr(si), _ptr(out), _ptr(it)))
+        return (out, it) if return_iters else out
+
+    def stack_batch(self, wmap, durations, starttimes, slips, nt, ns):
+        d, st, sl = _f64(durations), _f64(starttimes), _f64(slips)
+        B, npatch = d.shape
+        nvar = sl.shape[0]
+        if st.shape != (B, nt, npatch) or sl.shape != (nvar, B, npatch):
+            raise ValueError("stack_batch: inconsistent shapes")
+        out = np.empty((B, nt, ns))
+        self._check(self._lib.beatgpu_stack_batch(self._h, wmap, B, nvar, _ptr(d), _ptr(st), _ptr(sl), _ptr(out)))
+        return out
+
+    def misfit_batch(self, wmap, residuals, hypers):
+        r, h = _f64(residuals), _f64(hypers)
+        B, nt, _ = r.shape
+        if h.ndim != 2 or h.shape[0] != B:
+            raise ValueError("hypers must be [B, n_hypers]")
+        out = np.empty((B, nt))
+        self._check(self._lib.beatgpu_misfit_batch(self._h, wmap, B, _ptr(r), _ptr(h), h.shape[1], _ptr(out)))
+        return out
+
+    def ffi_loglike_batch(self, q, logpts=None, like=None):
+        """Host-pointer entry (copies in and out, synchronises).  q [B, n_params] float64 C-contiguous."""
+        q = _f64(q)
+        B = q.shape[0]
+        n_out = self.n_outputs()
+        if logpts is None:
+            logpts = np.empty((B, n_out))
+        if like is None:
+            like = np.empty(B)
+        self._check(self._lib.beatgpu_ffi_loglike_batch(self._h, B, _ptr(q), _ptr(logpts), _ptr(like)))
+        return logpts, like
+
+    def ffi_loglike_batch_ptr(self, B, q_ptr, logpts_ptr, like_ptr):
+        """Host-pointer entry on raw addresses (e.g. pinned torch tensors)."""
+        self._check(self._lib.beatgpu_ffi_loglike_batch(self._h, int(B), C.c_void_p(q_ptr), C.c_void_p(logpts_ptr),
+                                                        C.c_void_p(like_ptr)))
+
+    def ffi_loglike_batch_dev(self, B, q_dev_ptr, logpts_dev_ptr, like_dev_ptr):
+        """Device-pointer entry: enqueues on the ctx stream, no synchronisation."""
+        self._check(self._lib.beatgpu_ffi_loglike_batch_dev(self._h, int(B), C.c_void_p(q_dev_ptr), C.c_void_p(logpts_dev_ptr),
+                                                            C.c_void_p(like_dev_ptr or 0)))
+
+    def get_starttimes(self, B, npatches):
+        out = np.empty((B, npatches))
+        self._check(self._lib.beatgpu_get_starttimes(self._h, B, _ptr(out)))
+        return out
+
+    def index_violations(self):
+        n = C.c_int64()
+        self._check(self._lib.beatgpu_index_violations(self._h, C.byref(n)))
+        return n.value
+
+    def launch_count(self):
+        n = C.c_int64()
+        self._check(self._lib.beatgpu_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def last_stack_ms(self):
+        ms = C.c_float()
+        self._check(self._lib.beatgpu_last_stack_ms(self._h, C.byref(ms)))
+        return ms.value

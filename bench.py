@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""
+bench.py -- forward+loglike evals/s on the FFI seismic 200-patch configuration (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one lock-step evaluation of the hot path (fast sweep -> GF stack -> residual -> misfit -> like)
+for every chain held by a rank: C3 = 1 subfault 10x20 patches (2 km), 64 targets x 120 samples, library
+17 durations x 64 start times, slip components uparr+uperp, multilinear interpolation, exponential (Toeplitz)
+data covariance; 4000 chains per GPU (weak scaling: chains are independent, sharded across ranks, one NCCL
+all-gather of the per-chain llk per step for N > 1).  Synthetic GF libraries are generated directly in HBM.
+
+`value`  : chains/s with q already resident in HBM (device-pointer entry), CUDA events, max over ranks.
+`e2e`    : the same through the host-pointer C-ABI entry: pinned q -> H2D -> kernels -> D2H of logpts+like.
+`roofline`: GF-stacking kernel, algorithmic bytes / its CUDA-event duration vs measured HBM copy peak.
+`cpu_baseline` / `--impl reference`: the oracle's restatement of the reference CPU path (reference's own compiled
+fast_sweep_ext when oracle/_ref exists, numpy stack_all mode, numpy llk), one chain at a time, fanned out over the
+host cores with a fork pool the way the reference's paripool does -- a reported baseline, not the target.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "forward+loglike evals/sec (FFI seismic 200-patch)"
+UNIT = "evals/s"
+
+
+def c3_args(quick):
+    if quick:
+        return dict(nt=8, subfaults=((5, 8, 2.0),), ns=40, ndur=5, nst=40)
+    return dict(nt=64, subfaults=((10, 20, 2.0),), ns=120, ndur=17, nst=64)
+
+
+def workload_config(args, n_gpus, chains):
+    a = c3_args(args.quick)
+    nd, nstr, h = a["subfaults"][0]
+    return {
+        "workload": "C3 FFI seismic: %d patches (%dx%d, %.1f km) x %d targets x %d samples, library %d durations x %d "
+                    "starttimes, uparr+uperp, %s, exponential covariance" % (nd * nstr, nd, nstr, h, a["nt"], a["ns"],
+                                                                            a["ndur"], a["nst"], args.interpolation),
+        "chains_per_gpu": chains, "global_chains": chains * n_gpus, "parallelism": "chains sharded x%d" % n_gpus,
+        "gf_storage": args.store, "accumulate": "f64", "interpolation": args.interpolation,
+        "l2": "inputs>L2 (GF library %.1f GB per GPU; q rotates between steps)" % (lib_bytes(a, args.store) / 1e9),
+    }
+
+
+def lib_bytes(a, store):
+    nd, nstr, _ = a["subfaults"][0]
+    return 2 * a["nt"] * nd * nstr * a["ndur"] * a["nst"] * a["ns"] * (4 if store == "f32" else 8)
+
+
+def algorithmic_bytes_per_eval(a, store, interpolation):
+    nd, nstr, _ = a["subfaults"][0]
+    K = 4 if interpolation == "multilinear" else 1
+    return a["nt"] * nd * nstr * a["ns"] * K * 2 * (4 if store == "f32" else 8)
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline
+_CPU = {}
+
+
+def _cpu_eval(i):
+    from oracle import ffi_oracle
+    from beat_b200 import synthetic
+    q = _CPU["Q"][i]
+    return ffi_oracle.ffi_seismic_eval(_CPU["prob"], synthetic.split_point(_CPU["prob"], q), impl=_CPU["impl"]).sum()
+
+
+def build_cpu_problem(args):
+    """Same shapes as the GPU workload but only 2 duration nodes in the host library (bounded RAM / build time);
+    bytes gathered per evaluation are identical (nt*np*K*nvar rows of ns samples)."""
+    from beat_b200 import synthetic
+    a = c3_args(args.quick)
+    a = dict(a, ndur=2)
+    prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, **a)
+    return prob
+
+
+def cpu_baseline(args, n_evals_per_core=6, cores=None):
+    """Times the reference-style CPU path; returns (dict for the JSON line, evals/s)."""
+    import multiprocessing as mp
+    from beat_b200 import synthetic
+    from oracle import ffi_oracle
+    subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    cores = cores or os.cpu_count()
+    prob = build_cpu_problem(args)
+    n = max(cores, n_evals_per_core * cores)
+    Q = synthetic.draw_chains(prob, n, seed=999)
+    have_ref = ffi_oracle.load_reference_ext() is not None
+    _CPU.update(prob=prob, Q=Q, impl="ref" if have_ref else "port")
+    # single core
+    t0 = time.perf_counter()
+    n1 = max(2, min(8, n))
+    for i in range(n1):
+        _cpu_eval(i)
+    one = n1 / (time.perf_counter() - t0)
+    # all cores, chains fanned out over a fork pool (reference: beat/parallel.py:186-282)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_eval, range(cores))          # warm the workers
+        t0 = time.perf_counter()
+        pool.map(_cpu_eval, range(n), chunksize=max(1, n // (4 * cores)))
+        allc = n / (time.perf_counter() - t0)
+    info = {"value": allc, "unit": UNIT, "cores": cores, "kind": "port",
+            "value_1core": one,
+            "sample": "%d chains of the same C3 shapes (host library with 2 duration nodes, f64), one chain per call: "
+                      "%s fast_sweep + numpy stack_all (%s) + numpy mvn-chol llk, fork pool over %d cores"
+                      % (n, "reference's compiled" if have_ref else "C-restated", args.interpolation, cores)}
+    return info, allc
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    # K timed steps, each a bounded sample (cores*2 chains); W warm-up steps
+    import multiprocessing as mp
+    from beat_b200 import synthetic
+    from oracle import ffi_oracle
+    subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    prob = build_cpu_problem(args)
+    per_step = cores * 2
+    Q = synthetic.draw_chains(prob, per_step * (args.steps + args.warmup), seed=999)
+    have_ref = ffi_oracle.load_reference_ext() is not None
+    _CPU.update(prob=prob, Q=Q, impl="ref" if have_ref else "port")
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        k = 0
+        for _ in range(args.warmup):
+            pool.map(_cpu_eval, range(k, k + per_step))
+            k += per_step
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_cpu_eval, range(k, k + per_step))
+            k += per_step
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    a = c3_args(args.quick)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args, args.gpus, per_step), gf_storage="f64 (host)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d chains per step (bounded sample of the 4000-chain workload), same C3 shapes with 2 "
+                                   "duration nodes in the host library; %s fast_sweep + numpy stack_all + numpy llk, one "
+                                   "chain per call, fork pool over %d cores" % (per_step, "reference's compiled" if have_ref else "C-restated", cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0]))
+                mx = float(p[1])
+            except Exception:
+                continue
+            for nme, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+class _DevBuf:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def fill_library_on_device(ev, prob, torch, device, store):
+    """Generate the synthetic GF libraries straight into the HBM buffers owned by libbeatgpu."""
+    from beat_b200 import synthetic
+    for iw, wm in enumerate(prob["wavemaps"]):
+        dims = (wm["nt"], prob["npatches"], wm["ndur"], wm["nst"], wm["ns"])
+        for iv, v in enumerate(prob["slip_vars"]):
+            ptr, ld = ev.alloc_library(iw, iv, dims, wm["dur_min"], wm["dur_step"], wm["st_min"], wm["st_step"])
+            tdt = torch.float32 if store == "f32" else torch.float64
+            view = torch.as_tensor(_DevBuf(ptr, dims[:4] + (ld,), "<f4" if store == "f32" else "<f8"), device=device)
+            A = torch.from_numpy(wm["A"][v]).to(device)
+            k0 = torch.from_numpy(wm["k0"][v]).to(device)
+            tb = 2
+            for t0 in range(0, wm["nt"], tb):
+                blk = synthetic.library_block(A[t0:t0 + tb], k0[t0:t0 + tb], wm["ndur"], wm["nst"], wm["ns"], wm["st_step"],
+                                              prob["dt"], xp=torch, dtype=tdt)
+                view[t0:t0 + tb, :, :, :, :wm["ns"]] = blk
+                if ld > wm["ns"]:
+                    view[t0:t0 + tb, :, :, :, wm["ns"]:] = 0
+            del view
+    torch.cuda.synchronize(device)
+
+
+def run_gpu_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    n_gpus = max(1, world)
+
+    # CPU baseline first (fork pool before CUDA is initialised in this process), rank 0 at N=1 only
+    cpu_info = None
+    if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
+        cpu_info, _ = cpu_baseline(args)
+
+    import torch
+    import torch.distributed as dist
+    from beat_b200 import synthetic
+    from beat_b200.engine import BatchedFFILogLike
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the GPU arm has no CPU fallback (use --impl reference for the CPU path)")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if n_gpus > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    a = c3_args(args.quick)
+    B = args.chains
+    prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, build_library=False, **a)
+    ev = BatchedFFILogLike.from_problem(prob, device=local_rank, store_dtype="float32" if args.store == "f32" else "float64",
+                                        upload_libraries=False)
+    fill_library_on_device(ev, prob, torch, device, args.store)
+
+    n_rot = 3
+    Qs = [synthetic.draw_chains(prob, B, seed=4321 + 17 * rank + 1000 * r) for r in range(n_rot)]
+    q_dev = [torch.from_numpy(q).to(device) for q in Qs]
+    q_pin = [torch.from_numpy(q).pin_memory() for q in Qs]
+    n_out = ev.n_out
+    logpts_dev = torch.empty((B, n_out), dtype=torch.float64, device=device)
+    like_dev = torch.empty((B,), dtype=torch.float64, device=device)
+    like_all = torch.empty((n_gpus * B,), dtype=torch.float64, device=device) if n_gpus > 1 else None
+    logpts_pin = torch.empty((B, n_out), dtype=torch.float64).pin_memory()
+    like_pin = torch.empty((B,), dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def step_resident(i):
+        ev.eval_device(q_dev[i % n_rot], logpts_dev, like_dev)
+        if n_gpus > 1:
+            dist.all_gather_into_tensor(like_all, like_dev)      # the per-stage exchange of SMC (llk of every chain)
+
+    def step_e2e(i):
+        ev.eval_pinned(B, q_pin[i % n_rot].data_ptr(), logpts_pin.data_ptr(), like_pin.data_ptr())
+        if n_gpus > 1:
+            like_dev.copy_(like_pin, non_blocking=True)
+            dist.all_gather_into_tensor(like_all, like_dev)
+
+    # bind the ctx to torch's current stream so torch events bracket our kernels
+    ev.eval_device(q_dev[0], logpts_dev, like_dev)
+    torch.cuda.synchronize(device)
+    viol = ev.ctx.index_violations()
+    if viol:
+        raise SystemExit("bench.py: %d library index violations in the synthetic chains" % viol)
+    if not torch.isfinite(like_dev).all():
+        raise SystemExit("bench.py: non-finite llk in the synthetic chains")
+
+    # ---------------- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = ev.ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stack_ms = []
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(i)
+        if args.stack_timing == "per-step":
+            stack_ms.append(ev.ctx.last_stack_ms())       # event pair recorded inside the library around the stack kernel
+    e1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = e0.elapsed_time(e1)
+    if args.stack_timing != "per-step":
+        stack_ms.append(ev.ctx.last_stack_ms())
+    launches = ev.ctx.launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    if n_gpus > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = n_gpus * B * args.steps / (ms_total / 1e3)
+
+    # ---------------- e2e: host buffers through the C-ABI host entry
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if n_gpus > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_gpus * B * args.steps / (float(t.item()) / 1e3)
+    host_like = like_pin.numpy().copy()
+    assert np.isfinite(host_like).all()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        bytes_launch = algorithmic_bytes_per_eval(a, args.store, args.interpolation) * B
+        k_ms = float(np.mean(stack_ms))
+        achieved = bytes_launch / (k_ms / 1e3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "stack_kernel_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("chains") == B and tj.get("store") == args.store and tj.get("interpolation") == args.interpolation:
+                    traffic = tj.get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus, B),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * prob["n_params"] * 8,
+                    "d2h_bytes_per_step": B * (n_out + 1) * 8},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "gf_stack_misfit_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": k_ms,
+                         "kernel_share_of_step": k_ms / (ms_total / args.steps)},
+        }
+        if cpu_info is not None:
+            line["cpu_baseline"] = cpu_info
+        print(json.dumps(line))
+    ev.close()
+    if n_gpus > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="beat_b200", choices=["beat_b200", "reference"])
+    ap.add_argument("--chains", type=int, default=4000, help="chains per GPU")
+    ap.add_argument("--store", default="f32", choices=["f32", "f64"], help="GF library storage dtype in HBM")
+    ap.add_argument("--interpolation", default="multilinear", choices=["multilinear", "nearest_neighbor"])
+    ap.add_argument("--quick", action="store_true", help="tiny shapes (development only; not a valid benchmark)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stack-timing", default="per-step", choices=["per-step", "last"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,213 @@
+/*
+ * beatgpu.h -- C-ABI of libbeatgpu.so: the B200 (sm_100a) implementation of BEAT's per-chain
+ * forward model + log-likelihood hot path, batched over SMC/PT chains.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only; no torch,
+ * numpy or CUDA types in any signature.  Every entry point names the reference interface it
+ * replaces (paths relative to the hvasbath/beat tree, v2.0.5).  The reference side binds this
+ * with ctypes (our own binding is beat_b200/lib.py).
+ *
+ * Conventions
+ *  - all functions return 0 on success, a BEATGPU_E_* code otherwise; beatgpu_last_error()
+ *    gives the message.  Nothing is clamped or silently repaired: out-of-range library indices
+ *    and non-finite results are reported (the reference would raise IndexError / ValueError,
+ *    beat/ffi/base.py:650-674, beat/sampler/metropolis.py:279-284).
+ *  - "host" entry points take HOST pointers, copy in/out and synchronise before returning.
+ *    "_dev" entry points take DEVICE pointers, enqueue on the context's stream and do not
+ *    synchronise (call beatgpu_sync()).
+ *  - arrays are C-contiguous (row-major), float64 unless said otherwise; B = number of chains.
+ *  - a context belongs to one (process, GPU); calls on one context are serialised on its stream;
+ *    it is not fork-safe (the reference forks workers, beat/parallel.py:243 -- the batched path
+ *    runs with n_jobs=1, one process per GPU).
+ *  - the library never frees or retains caller memory; all device scratch is owned by the ctx and
+ *    grown on demand (no cudaMalloc on the steady-state path once B is stable).
+ */
+#ifndef BEATGPU_H
+#define BEATGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEATGPU_VERSION 100          /* 0.1.0 */
+#define BEATGPU_MAX_SLIPVARS 3       /* uparr, uperp, utens  (beat/config.py:83-94) */
+
+/* status codes */
+#define BEATGPU_OK            0
+#define BEATGPU_E_CUDA        1      /* CUDA runtime error (message has the detail)          */
+#define BEATGPU_E_ARG         2      /* bad argument / call order                             */
+#define BEATGPU_E_INDEX       3      /* a GF-library index left the library (IndexError)      */
+#define BEATGPU_E_NOTREADY    4      /* an operand required by the call has not been uploaded */
+#define BEATGPU_E_NONFINITE   5      /* reserved: non-finite llk (ValueError in the sampler)  */
+
+/* storage dtype of a GF library on the device */
+#define BEATGPU_F32 0
+#define BEATGPU_F64 1
+
+/* interpolation of rupture start time / rise time into the library
+ * (beat/config.py:571-575; beat/ffi/base.py:506-517,553-564,649-698) */
+#define BEATGPU_NEAREST      0
+#define BEATGPU_MULTILINEAR  1
+
+typedef struct beatgpu_ctx beatgpu_ctx;
+
+/* ---------------------------------------------------------------- context ------------------ */
+int         beatgpu_version(void);
+int         beatgpu_ctx_create(int device, beatgpu_ctx** out);
+void        beatgpu_ctx_destroy(beatgpu_ctx* ctx);
+const char* beatgpu_last_error(const beatgpu_ctx* ctx);    /* ctx may be NULL: last create() error */
+int         beatgpu_sync(beatgpu_ctx* ctx);                 /* cudaStreamSynchronize on the ctx stream */
+/* make the ctx enqueue on an existing CUDA stream (e.g. torch's current stream); 0 = own stream */
+int         beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream);
+/* number of SMs, device name; for sizing/reporting */
+int         beatgpu_device_info(beatgpu_ctx* ctx, int* n_sm, char* name, int name_len);
+
+/* ---------------------------------------------------------------- static operands ----------
+ * These replace the pytensor shared variables the reference builds once in
+ * Composite.get_formula (beat/models/seismic.py:1210-1349, geodetic.py:1030-1084,
+ * laplacian.py:40-62) and updates between SMC stages (seismic.py:1509-1534).               */
+
+/* Fault discretisation: per subfault the patch grid and (square) patch size [km].
+ * Replaces FaultGeometry.ordering / Sweeper.__init__ (beat/pytensorf.py:426-430,
+ * beat/models/seismic.py:1097-1111).  Patch order inside a subfault is dip-major:
+ * flat = dip * n_patch_strike + strike (beat/pytensorf.py:475-482).                          */
+int beatgpu_set_fault(beatgpu_ctx* ctx, int n_subfaults, const int32_t* n_patch_dip,
+                      const int32_t* n_patch_strike, const double* patch_size_km);
+
+/* How a chain's flat parameter vector q[n_params] maps onto the model variables; replaces pymc's
+ * DictToArrayBijection over value_vars (beat/backend.py:147,163-165; variable list
+ * beat/config.py:1506-1542).  An offset of -1 means "not sampled": the value comes from
+ * `fixed` (the reference's fixed_rvs, seismic.py:1243).  Lengths are implied by the fault
+ * (npatches, n_subfaults) and by n_hypers / n_time_shifts.                                   */
+typedef struct beatgpu_layout {
+    int32_t n_params;
+    int32_t n_slipvars;                        /* 1..3, order = slip_varnames                 */
+    int32_t off_slip[BEATGPU_MAX_SLIPVARS];    /* each [npatches]                             */
+    int32_t off_durations;                     /* [npatches]                                  */
+    int32_t off_velocities;                    /* [npatches]                                  */
+    int32_t off_nucleation_strike;             /* [n_subfaults]                               */
+    int32_t off_nucleation_dip;                /* [n_subfaults]                               */
+    int32_t off_time;                          /* [n_subfaults]                               */
+    int32_t off_hypers;                        /* [n_hypers]  (h_* in canonical order)        */
+    int32_t n_hypers;
+    int32_t off_time_shifts;                   /* [n_time_shifts] hierarchical station corr.  */
+    int32_t n_time_shifts;
+} beatgpu_layout;
+/* fixed: canonical vector [nslip*np | np | np | nsf | nsf | nsf | n_hypers | n_time_shifts] used for
+ * every variable whose offset is -1 (may be NULL if nothing is fixed).                        */
+int beatgpu_set_layout(beatgpu_ctx* ctx, const beatgpu_layout* layout, const double* fixed);
+
+/* Declare one seismic wavemap (a WaveformMapping: beat/heart.py:2884-3148) with n_targets
+ * datasets of n_samples each.  station_idx[n_targets] maps a target to its entry of the
+ * time_shifts hierarchical (wmap.station_correction_idxs, seismic.py:1283-1291) or is NULL.
+ * hyper_idx[n_targets] indexes the hypers block (hp_specific or not: distributions.py:121-126).
+ * nsamples[n_targets] is dataset.samples (M, distributions.py:120).  Returns the wavemap id in
+ * *wmap_id; datasets are appended to the output row in declaration order (seismic.py:1348).   */
+int beatgpu_add_wavemap(beatgpu_ctx* ctx, int n_targets, int n_samples, int interpolation,
+                        const int32_t* station_idx, const int32_t* hyper_idx,
+                        const int32_t* nsamples, int* wmap_id);
+
+/* Upload one slip component's GF library: traces laid out (ntargets, npatches, ndurations,
+ * nstarttimes, nsamples) C-order exactly as the reference's `.traces.npy`
+ * (beat/ffi/base.py:161-189,378) of dtype src_dtype, stored on the device as store_dtype
+ * (BEATGPU_F64 = strict parity mode, BEATGPU_F32 = half the bytes).  Axis origin/step are
+ * SeismicGFLibraryConfig.duration_min/duration_sampling/starttime_min/starttime_sampling
+ * (beat/config.py:1900-1919).  `traces` may be a memory-mapped file; it is streamed in chunks.
+ * Replaces SeismicGFLibrary.init_optimization (beat/ffi/base.py:387-404).                    */
+int beatgpu_upload_gflib(beatgpu_ctx* ctx, int wmap_id, int slipvar, const void* traces,
+                         int src_dtype, int store_dtype, const int64_t dims[5],
+                         double duration_min, double duration_step,
+                         double starttime_min, double starttime_step);
+/* Allocate the library on the device without filling it and hand back the raw device pointer
+ * (store_dtype elements, row stride *row_stride elements) so a caller can generate / copy
+ * a library device-side (bench: synthetic libraries are built directly in HBM).              */
+int beatgpu_alloc_gflib(beatgpu_ctx* ctx, int wmap_id, int slipvar, int store_dtype,
+                        const int64_t dims[5], double duration_min, double duration_step,
+                        double starttime_min, double starttime_step,
+                        void** device_ptr, int64_t* row_stride);
+
+/* Observed data, one row per target: wmap.shared_data_array (beat/heart.py:3126-3133).      */
+int beatgpu_upload_data(beatgpu_ctx* ctx, int wmap_id, const double* data /*[nt, ns]*/);
+
+/* Weights = Covariance.chol_inverse (upper-triangular U with U^T U = C^-1, beat/heart.py:211-237)
+ * and slog_pdet = Covariance.log_pdet (:239-245) for every target of the wavemap; called at
+ * setup (SeismicComposite.init_weights, seismic.py:363-378) and again between SMC stages
+ * (update_weights, seismic.py:1527-1534).  The library inspects U: entries whose magnitude is
+ * below band_rtol * max|U| are treated as structural zeros, and U is stored as diagonal,
+ * upper-banded (Toeplitz `exponential` noise gives bandwidth 1) or dense.  band_rtol < 0
+ * selects the default (1e-13); band_rtol = 0 forces exact structure detection.               */
+int beatgpu_update_weights(beatgpu_ctx* ctx, int wmap_id, const double* U /*[nt, ns, ns]*/,
+                           const double* slog_pdet /*[nt]*/, double band_rtol);
+
+/* Geodetic static composite (beat/models/geodetic.py:1030-1084): one library per slip var,
+ * G[var] (npatches, nobs) as GeodeticGFLibrary (beat/ffi/base.py:192-305); data and odw [nobs];
+ * n_datasets slices [lo, hi) of the concatenated observation vector (Bij.srmap); U per dataset
+ * concatenated (sum n_i^2 doubles), slog_pdet, nsamples, hyper_idx per dataset.             */
+int beatgpu_set_geodetic(beatgpu_ctx* ctx, int n_obs, int n_datasets, const int32_t* slice_lo,
+                         const int32_t* slice_hi, const double* const* G /*[n_slipvars] each [np, nobs]*/,
+                         const double* data, const double* odw, const double* U_concat,
+                         const double* slog_pdet, const int32_t* nsamples, const int32_t* hyper_idx);
+int beatgpu_update_geodetic_weights(beatgpu_ctx* ctx, const double* U_concat, const double* slog_pdet);
+
+/* Laplacian smoothing prior (beat/models/laplacian.py:40-139): operator L (npatches, npatches),
+ * sdet = log_determinant(L.T * L) (:57-60) and the index of h_laplacian in the hypers block.  */
+int beatgpu_set_laplacian(beatgpu_ctx* ctx, const double* L, double sdet, int hyper_idx);
+
+/* Number of outputs per chain: seismic datasets of all wavemaps, then geodetic datasets, then one
+ * laplacian_like (if set) -- the per-dataset logpts the reference traces store
+ * (seis_like / geo_like / laplacian_like, beat/sampler/metropolis.py:160-162).              */
+int beatgpu_n_outputs(beatgpu_ctx* ctx, int* n_out);
+
+/* ---------------------------------------------------------------- hot path ----------------- */
+
+/* Batched Sweeper: replaces Sweeper.perform -> fast_sweep_ext.fast_sweep
+ * (beat/pytensorf.py:443-500, beat/fast_sweeping/fast_sweep_ext.c:120-206) for B chains of one
+ * subfault.  slowness [B, np_sf] (= 1/velocities), nuc_dip_idx / nuc_strike_idx [B] patch indices;
+ * out start times [B, np_sf] (no `time` offset added, exactly like the Op).
+ * n_iter [B] (optional, may be NULL) receives the outer iteration count.                     */
+int beatgpu_fast_sweep_batch(beatgpu_ctx* ctx, int subfault, int B, const double* slowness,
+                             const int32_t* nuc_dip_idx, const int32_t* nuc_strike_idx,
+                             double* starttimes, int32_t* n_iter);
+
+/* Batched SeismicGFLibrary.stack_all (beat/ffi/base.py:607-709) summed over the wavemap's slip
+ * components as the composite does (seismic.py:1317-1330): durations [B, np], starttimes
+ * [B, nt, np], slips [n_slipvars, B, np]  ->  synthetics [B, nt, ns].  n_slipvars_used <=
+ * uploaded libraries; interpolation as declared for the wavemap.                              */
+int beatgpu_stack_batch(beatgpu_ctx* ctx, int wmap_id, int B, int n_slipvars_used,
+                        const double* durations, const double* starttimes, const double* slips,
+                        double* synthetics);
+
+/* Batched multivariate_normal_chol (beat/models/distributions.py:72-140) for one wavemap:
+ * residuals [B, nt, ns], hypers [B, n_hypers]  ->  logpts [B, nt].                             */
+int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* residuals,
+                         const double* hypers, int n_hypers, double* logpts);
+
+/* The fused evaluation: replaces one call of the compiled logp_forw_func(q)
+ * (beat/sampler/base.py:598-615; graph of seismic.py:1253-1349 [+ geodetic.py:1065-1084,
+ * laplacian.py:98-139]) for each of B chains: q [B, n_params] -> logpts [B, n_out] and
+ * like [B] = row sums (beat/models/problems.py:228-247).                                       */
+int beatgpu_ffi_loglike_batch(beatgpu_ctx* ctx, int B, const double* q, double* logpts, double* like);
+int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q_dev, double* logpts_dev,
+                                  double* like_dev);
+
+/* After a loglike batch: per-chain rupture start times [B, npatches] (Deterministic-style
+ * inspection / parity of the sweep inside the fused path); host pointer.                     */
+int beatgpu_get_starttimes(beatgpu_ctx* ctx, int B, double* starttimes);
+
+/* Count of (chain, target, patch) taps that fell outside a library since the last call of this
+ * function (the counter is reset).  Affected logpts are NaN.                                  */
+int beatgpu_index_violations(beatgpu_ctx* ctx, int64_t* count);
+
+/* Counters for reporting: kernels launched by this ctx since creation.                       */
+int beatgpu_launch_count(beatgpu_ctx* ctx, int64_t* n_launches);
+
+/* Time the most recent fused evaluation's dominant kernel (gf stack + misfit) on the ctx stream
+ * with CUDA events: milliseconds of the last loglike batch's stack kernel(s).                */
+int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEATGPU_H */

@@ -1,0 +1,321 @@
+"""GPU parity tests (-m gpu): every CUDA path, called through the C-ABI, against the CPU oracle and the
+golden vectors produced by the reference's own code.  Integer/index work is bit-exact; float tolerances are
+written next to each assertion (north star: llk rtol 1e-5; the reference's own stack tolerance is 5e-6)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from beat_b200 import synthetic  # noqa: E402
+from oracle import ffi_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from beat_b200.lib import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def _oracle_logpts(prob, Q, impl="port"):
+    return np.array([O.ffi_seismic_eval(prob, synthetic.split_point(prob, q), impl=impl) for q in Q])
+
+
+# ------------------------------------------------------------------------------------------ fast sweeping
+def test_sweep_golden_reference_c(golden):
+    """CUDA sweep vs the reference's compiled C on the golden cases: <= 4 ulp (pow(x,.5) vs sqrt), same indices."""
+    from beat_b200.lib import Context
+    for i in range(int(golden["fs_ncases"])):
+        nd, ns, nuc_dip, nuc_strike = (int(v) for v in golden[f"fs{i}_meta"])
+        c = Context(0)
+        c.set_fault([nd], [ns], [float(golden[f"fs{i}_h"])])
+        t = c.fast_sweep_batch(0, golden[f"fs{i}_slow"][None, :], [nuc_dip], [nuc_strike])[0]
+        ref = golden[f"fs{i}_t_c"]
+        assert np.all(np.abs(t - ref) <= 4 * np.spacing(np.abs(ref))), i
+        np.testing.assert_allclose(t, golden[f"fs{i}_t_numpy"], rtol=0, atol=1e-6)   # reference's own gate
+        for interp in ("nearest_neighbor", "multilinear"):
+            assert np.array_equal(O.times2idxs(t, -5.0, 0.5, interp)[0], O.times2idxs(ref, -5.0, 0.5, interp)[0])
+        c.close()
+
+
+@pytest.mark.parametrize("nd,ns,h", [(10, 20, 2.0), (10, 15, 2.5), (1, 7, 1.0), (9, 1, 3.0), (24, 40, 1.0), (40, 33, 0.5)])
+def test_sweep_bitexact_vs_port(nd, ns, h):
+    """Anti-diagonal wavefront schedule == sequential Gauss-Seidel, bit for bit, incl. the iteration count."""
+    from beat_b200.lib import Context
+    rng = np.random.default_rng(nd * 100 + ns)
+    B = 3000
+    slow = 1.0 / rng.uniform(2.2, 4.5, (B, nd * ns))
+    slow[: B // 10] = 1.0 / rng.uniform(0.3, 6.0, (B // 10, nd * ns))      # rough media -> more outer iterations
+    hr, hc = rng.integers(0, nd, B), rng.integers(0, ns, B)
+    c = Context(0)
+    c.set_fault([nd], [ns], [h])
+    got, it = c.fast_sweep_batch(0, slow, hr, hc, return_iters=True)
+    ref, it_ref = O.fast_sweep_batch_port(slow, h, hr, hc, nd, ns)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(it, it_ref)
+    c.close()
+
+
+def test_sweeper_op_reference_test_case():
+    """Mirror of test/test_fastsweep.py:84-112 (`_pytensor_c_wrapper`) with the GPU Op."""
+    from beat_b200.ops import Sweeper
+    patch_size, nuc_x, nuc_y, n_patch_strike, n_patch_dip = 10.0, 2, 3, 4, 6
+    velocities = np.concatenate((np.ones((n_patch_dip, 2)), np.ones((n_patch_dip, 2)) * 3.5), axis=1)
+    slownesses = 1.0 / velocities
+    cleanup = Sweeper(patch_size, n_patch_dip, n_patch_strike, "cuda")
+    out = [[None]]
+    cleanup.perform(None, [slownesses.flatten(), nuc_y, nuc_x], out)
+    c_i = O.fast_sweep(slownesses.flatten(), patch_size, nuc_y, nuc_x, n_patch_dip, n_patch_strike, impl="port")
+    np.testing.assert_allclose(out[0][0], c_i, rtol=0.0, atol=1e-6)
+    assert np.array_equal(out[0][0], c_i)
+    np.testing.assert_allclose(out[0][0].reshape(6, 4)[3], [20.0, 10.0, 0.0, 2.8571428571428568], atol=1e-13)
+    with pytest.raises(NotImplementedError):
+        Sweeper(patch_size, n_patch_dip, n_patch_strike, "fortran").perform(None, [slownesses.flatten(), 3, 2], [[None]])
+    with pytest.raises(IndexError):
+        cleanup.perform(None, [slownesses.flatten(), 6, 2], [[None]])     # nucleation outside the grid
+
+
+# ------------------------------------------------------------------------------------------ stacking
+@pytest.mark.parametrize("name", ["rand", "recipe"])
+@pytest.mark.parametrize("tag,interp", [("nn", "nearest_neighbor"), ("ml", "multilinear")])
+@pytest.mark.parametrize("store,rtol", [("float64", 1e-12), ("float32", 5e-6)])
+def test_stack_all_golden(golden, name, tag, interp, store, rtol):
+    """SeismicGFLibrary.stack_all on the GPU vs the reference's own numpy stack_all output."""
+    from beat_b200.ops import SeismicGFLibrary
+    st_min, st_step, dur_min, dur_step = golden["stack_axes"]
+    G = golden[f"stack_{name}_G"]
+    gfs = SeismicGFLibrary(G, dur_min, dur_step, st_min, st_step, store_dtype=store)
+    d, s, u = golden[f"stack_{name}_durations"], golden[f"stack_{name}_starttimes"], golden[f"stack_{name}_slips"]
+    tidx = np.atleast_2d(np.arange(G.shape[0])).T
+    got = gfs.stack_all(d, s, u, targetidxs=tidx, interpolation=interp)
+    ref = golden[f"stack_{name}_{tag}"]
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=rtol * np.abs(ref).max())
+    with pytest.raises(ValueError):
+        gfs.stack_all(d, s, u, interpolation=interp)                       # targetidxs mandatory (base.py:630-631)
+    with pytest.raises(NotImplementedError):
+        gfs.stack_all(d, s, u, targetidxs=tidx, interpolation="cubic")
+
+
+def test_stack_batch_random_vs_oracle():
+    """Batched stacking, two components summed, ragged sizes (ns not a multiple of 4, > one 128-sample window)."""
+    from beat_b200.ops import SeismicGFLibrary
+    rng = np.random.default_rng(8)
+    for (nt, npatch, ndur, nst, ns) in [(3, 7, 3, 6, 10), (2, 300, 2, 5, 8), (2, 5, 3, 4, 150), (1, 1, 2, 2, 1)]:
+        G = {"uparr": rng.standard_normal((nt, npatch, ndur, nst, ns)), "uperp": rng.standard_normal((nt, npatch, ndur, nst, ns))}
+        axes = dict(dur_min=0.5, dur_step=0.25, st_min=-1.0, st_step=0.5)
+        B = 5
+        d = rng.uniform(0.5 + 1e-3, 0.5 + (ndur - 1) * 0.25, (B, npatch))
+        s = rng.uniform(-1.0 + 1e-3, -1.0 + (nst - 1) * 0.5, (B, nt, npatch))
+        u = {k: rng.uniform(0, 3, (B, npatch)) for k in G}
+        tidx = np.atleast_2d(np.arange(nt)).T
+        for store, rtol in (("float64", 1e-12), ("float32", 5e-6)):
+            gfs = SeismicGFLibrary(G, 0.5, 0.25, -1.0, 0.5, store_dtype=store)
+            for interp in ("nearest_neighbor", "multilinear"):
+                got = gfs.stack_all(d, s, u, targetidxs=tidx, interpolation=interp)
+                for b in range(B):
+                    ref = sum(O.stack_all(G[k], d[b], s[b], u[k][b], axes["dur_min"], axes["dur_step"], axes["st_min"],
+                                          axes["st_step"], interp) for k in G)
+                    np.testing.assert_allclose(got[b], ref, rtol=rtol, atol=rtol * np.abs(ref).max())
+
+
+def test_stack_out_of_library_raises():
+    from beat_b200.ops import SeismicGFLibrary
+    rng = np.random.default_rng(0)
+    G = rng.standard_normal((2, 3, 3, 4, 8))
+    gfs = SeismicGFLibrary(G, 0.5, 0.25, 0.0, 0.5, store_dtype="float64")
+    tidx = np.atleast_2d(np.arange(2)).T
+    d, u = np.full(3, 0.7), np.ones(3)
+    with pytest.raises(IndexError):
+        gfs.stack_all(d, np.full((2, 3), 5.0), u, targetidxs=tidx, interpolation="multilinear")   # beyond last start time
+    with pytest.raises(IndexError):
+        gfs.stack_all(d, np.full((2, 3), -0.7), u, targetidxs=tidx, interpolation="nearest_neighbor")
+    # exactly on the first grid node: the zero-weight floor tap must not count as a violation
+    got = gfs.stack_all(np.full(3, 0.5), np.zeros((2, 3)), u, targetidxs=tidx, interpolation="multilinear")
+    np.testing.assert_allclose(got, G[:, :, 0, 0, :].sum(axis=1), rtol=1e-13)
+
+
+# ------------------------------------------------------------------------------------------ misfit
+def test_mvn_chol_golden(golden):
+    """multivariate_normal_chol on the GPU vs the reference's own output (diag, banded and dense weights mixed)."""
+    import types
+    from beat_b200.ops import multivariate_normal_chol
+    C, U, lp, res = golden["mvn_C"], golden["mvn_U"], golden["mvn_logpdet"], golden["mvn_res"]
+    n_t, ns = res.shape
+    datasets = [types.SimpleNamespace(samples=ns, typ="any_P_T", covariance=types.SimpleNamespace(slog_pdet=lp[i], log_pdet=lp[i]))
+                for i in range(n_t)]
+    got = multivariate_normal_chol(datasets, list(U), {"h_any_P_T": float(golden["mvn_h_scalar"])}, res)
+    np.testing.assert_allclose(got, golden["mvn_logpts_scalar"], rtol=1e-12)
+    got = multivariate_normal_chol(datasets, list(U), {"h_any_P_T": golden["mvn_h_vec"]}, res, hp_specific=True)
+    np.testing.assert_allclose(got, golden["mvn_logpts_vec"], rtol=1e-12)
+    # each structure on its own (diag-only -> DIAG path, exponential-only -> BAND path)
+    for sel in ([0, 1], [2, 3], [4, 5]):
+        ds = [datasets[i] for i in sel]
+        got = multivariate_normal_chol(ds, [U[i] for i in sel], {"h_any_P_T": float(golden["mvn_h_scalar"])}, res[sel])
+        np.testing.assert_allclose(got, golden["mvn_logpts_scalar"][sel], rtol=1e-12)
+
+
+def test_mvn_chol_vs_scipy_batched():
+    """Property the reference tests (test/test_models.py:149-222), batched over chains."""
+    import scipy.stats
+    import types
+    from beat_b200.covariance import Covariance, exponential_data_covariance
+    from beat_b200.ops import multivariate_normal_chol
+    rng = np.random.default_rng(2)
+    n_t, ns, B = 4, 50, 7
+    Cs = [exponential_data_covariance(ns, 0.5, 2.0 + i) * 0.2 ** 2 for i in range(n_t)]
+    covs = [Covariance(data=c) for c in Cs]
+    datasets = [types.SimpleNamespace(samples=ns, typ="any_P_Z", covariance=c) for c in covs]
+    res = rng.standard_normal((B, n_t, ns))
+    h = rng.uniform(0, 2, B)
+    got = multivariate_normal_chol(datasets, [c.chol_inverse for c in covs], {"h_any_P_Z": h}, res)
+    for b in range(B):
+        for i in range(n_t):
+            ref = scipy.stats.multivariate_normal.logpdf(res[b, i], mean=np.zeros(ns), cov=Cs[i] * np.exp(2 * h[b]))
+            assert abs(got[b, i] - ref) <= 1e-9 * abs(ref)
+
+
+# ------------------------------------------------------------------------------------------ fused path
+CASES = {
+    "ml_exp": dict(),
+    "nn_exp": dict(interpolation="nearest_neighbor"),
+    "ml_variance": dict(noise="variance"),
+    "ml_dense": dict(noise="dense"),
+    "station_corr_hp_specific": dict(station_corrections=True, hp_specific=True),
+    "two_subfaults": dict(subfaults=((4, 5, 2.0), (3, 6, 2.5))),
+    "three_slipvars": dict(slip_vars=("uparr", "uperp", "utens")),
+    "one_slipvar": dict(slip_vars=("uparr",)),
+    "two_wavemaps": dict(n_wavemaps=2),
+    "long_traces": dict(ns=300, nt=3),
+    "many_patches": dict(subfaults=((12, 25, 1.0),), nt=2, ns=16),
+    "odd_ns": dict(ns=37),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("store,rtol", [("float64", 1e-10), ("float32", 1e-5)])
+def test_fused_loglike_vs_oracle(case, store, rtol):
+    """q -> per-dataset logpts and like, all chains, vs the oracle's restatement of the reference graph."""
+    from beat_b200.engine import BatchedFFILogLike
+    args = dict(nt=5, subfaults=((4, 6, 2.0),), ns=32, ndur=4, seed=100 + sorted(CASES).index(case))
+    args.update(CASES[case])
+    prob = synthetic.make_problem(**args)
+    B = 24
+    Q = synthetic.draw_chains(prob, B, seed=5)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype=store)
+    logpts, like = ev(Q)
+    ref = _oracle_logpts(prob, Q)
+    assert logpts.shape == ref.shape
+    np.testing.assert_allclose(logpts, ref, rtol=rtol)
+    np.testing.assert_allclose(like, ref.sum(axis=1), rtol=rtol)
+    # rupture start times of the fused path are bit-identical to the sequential C restatement
+    st = ev.starttimes(B)
+    for b in range(0, B, 7):
+        _, _, t0 = O.ffi_seismic_eval(prob, synthetic.split_point(prob, Q[b]), impl="port", return_synth=True)
+        assert np.array_equal(st[b], t0)
+    # single-chain call, reference return convention
+    out = ev.logp_forw_func(Q[3])
+    np.testing.assert_allclose(out[0], ref[3], rtol=rtol)
+    assert ev.ctx.launch_count() > 0
+    ev.close()
+
+
+def test_fused_joint_geodetic_laplacian():
+    """Config-4 shape: seismic + geodetic static (dense non-Toeplitz C) + laplacian prior, all in one call."""
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=4, subfaults=((5, 7, 2.0),), ns=24, ndur=4, geodetic=dict(nobs=[60, 45]), laplacian=True, seed=3)
+    B = 16
+    Q = synthetic.draw_chains(prob, B, seed=6)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    logpts, like = ev(Q)
+    assert logpts.shape == (B, 4 + 2 + 1)
+    for b in range(B):
+        pt = synthetic.split_point(prob, Q[b])
+        ref = np.concatenate([O.ffi_seismic_eval(prob, pt, impl="port"), O.ffi_geodetic_eval(prob["geodetic"], pt),
+                              [O.ffi_laplacian_eval(prob["laplacian"], pt, prob["slip_vars"])]])
+        np.testing.assert_allclose(logpts[b], ref, rtol=1e-10)
+        np.testing.assert_allclose(like[b], ref.sum(), rtol=1e-10)
+    ev.close()
+
+
+def test_fused_fixed_variables():
+    """Variables absent from q (the reference's fixed_rvs) come from the `fixed` vector."""
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=3, subfaults=((4, 5, 2.0),), ns=20, ndur=4, seed=9)
+    B = 6
+    Q = synthetic.draw_chains(prob, B, seed=1)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    full, _ = ev(Q)
+    # fix durations and time to chain 0's values; drop them from q
+    npatch = prob["npatches"]
+    keep = [n for n, _ in prob["var_order"] if n not in ("durations", "time")]
+    sizes = dict(prob["var_order"])
+    prob2 = dict(prob)
+    offs, o = {}, 0
+    for n in keep:
+        offs[n] = o
+        o += sizes[n]
+    prob2["offsets"], prob2["n_params"] = offs, o
+    nsl, nsf = len(prob["slip_vars"]), len(prob["subfaults"])
+    fixed = np.zeros(nsl * npatch + 2 * npatch + 3 * nsf + prob["n_hypers"] + prob["n_time_shifts"])
+    fixed[nsl * npatch: (nsl + 1) * npatch] = Q[0, prob["offsets"]["durations"]: prob["offsets"]["durations"] + npatch]
+    fixed[(nsl + 2) * npatch + 2 * nsf: (nsl + 2) * npatch + 3 * nsf] = Q[0, prob["offsets"]["time"]: prob["offsets"]["time"] + nsf]
+    prob2["fixed"] = fixed
+    Q2 = np.concatenate([Q[:, prob["offsets"][n]: prob["offsets"][n] + sizes[n]] for n in keep], axis=1)
+    ev2 = BatchedFFILogLike.from_problem(prob2, store_dtype="float64")
+    got, _ = ev2(Q2)
+    Qref = Q.copy()
+    Qref[:, prob["offsets"]["durations"]: prob["offsets"]["durations"] + npatch] = Q[0, prob["offsets"]["durations"]: prob["offsets"]["durations"] + npatch]
+    Qref[:, prob["offsets"]["time"]: prob["offsets"]["time"] + nsf] = Q[0, prob["offsets"]["time"]: prob["offsets"]["time"] + nsf]
+    ref, _ = ev(Qref)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got[0], full[0])
+    ev.close()
+    ev2.close()
+
+
+def test_fused_violation_and_update_weights():
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=3, subfaults=((4, 5, 2.0),), ns=20, ndur=4, seed=21)
+    Q = synthetic.draw_chains(prob, 8, seed=2)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    base, _ = ev(Q)
+    # weights update between SMC stages (seismic.py:1527-1534): scaling C by 4 -> U/2, log_pdet + ns*log(4)
+    wm = prob["wavemaps"][0]
+    ev.update_weights(0, wm["U"] / 2.0, wm["slog_pdet"] + wm["ns"] * np.log(4.0))
+    prob2 = dict(prob)
+    wm2 = dict(wm, U=wm["U"] / 2.0, slog_pdet=wm["slog_pdet"] + wm["ns"] * np.log(4.0))
+    prob2["wavemaps"] = [wm2]
+    got, _ = ev(Q)
+    np.testing.assert_allclose(got, _oracle_logpts(prob2, Q), rtol=1e-10)
+    assert not np.allclose(got, base)
+    # a chain whose origin time pushes start times off the library axis -> IndexError, like the reference
+    Qbad = Q.copy()
+    Qbad[2, prob["offsets"]["time"]] = 1e4
+    with pytest.raises(IndexError):
+        ev(Qbad)
+    # nucleation point outside the fault -> IndexError as well
+    Qbad = Q.copy()
+    Qbad[1, prob["offsets"]["nucleation_dip"]] = 1e3
+    with pytest.raises(IndexError):
+        ev(Qbad)
+    # the context stays usable
+    got2, _ = ev(Q)
+    assert np.array_equal(got, got2)
+    ev.close()
+
+
+def test_device_resident_entry_matches_host_entry():
+    import torch
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=4, subfaults=((4, 6, 2.0),), ns=32, ndur=4, seed=33)
+    Q = synthetic.draw_chains(prob, 32, seed=3)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float32")
+    host_lp, host_like = ev(Q)
+    q_dev = torch.from_numpy(Q).cuda()
+    lp, like = ev.eval_device(q_dev)
+    torch.cuda.synchronize()
+    assert np.array_equal(lp.cpu().numpy(), host_lp)
+    assert np.array_equal(like.cpu().numpy(), host_like)
+    assert ev.ctx.last_stack_ms() > 0
+    ev.close()
