@@ -1,0 +1,232 @@
+"""
+Lock-step batched Metropolis / SMC driver: the shim that lets the batched GPU evaluator serve the reference's
+sampler logic.
+
+The reference advances ONE chain per ``Metropolis.astep`` call (beat/sampler/metropolis.py:276-422) and
+parallelises chains over forked processes (beat/sampler/base.py:428-595).  Here every chain of the population
+takes the same step at the same time:
+
+    for step in range(n_steps):
+        q      = q0 + proposal_sample * scaling                    (metropolis.py:311,325)
+        inside = prior bounds check                                 (metropolis.py:341-343; Uniform priors ->
+                                                                     finite prior logp <=> inside the box)
+        lp     = ONE batched GPU evaluation of all chains           (metropolis.py:349)
+        accept = log(u) < beta * (lp - l0)   (pymc metrop_select)   (metropolis.py:355-358)
+        per-chain scale tuning every tune_interval steps            (metropolis.py:294-306, pymc ``tune``)
+
+Stage logic is the reference's, restated on whole-population arrays: ``calc_beta`` (beat/sampler/smc.py:133-165),
+``calc_covariance`` (:167-186), Kitagawa ``resample`` (:290-324), the stage loop of ``smc_sample`` (:459-546)
+including the final stage.  Per-chain RNG streams are not bitwise those of the reference (it seeds each forked
+chain separately, sampler/base.py:515-516) -- the claim is distributional equivalence, tested on the reference's
+own toy posterior (test/test_smc.py).  Trace storage / checkpointing stay with the reference (out of scope).
+
+All population state lives in torch tensors on the evaluator's device; the only host round-trip per stage is the
+scalar bisection for beta.  With several ranks (torch.distributed) each rank advances its shard and the
+population-wide quantities are all-gathered once per stage (beat_b200.distributed).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def tune_scale(scale, acc_rate):
+    """pymc's Metropolis ``tune`` rule, used by the reference as ``step_tune`` (metropolis.py:300-302), vectorised.
+
+    Rate    Variance adaptation
+    <0.001  x 0.1 ; <0.05  x 0.5 ; <0.2  x 0.9 ; >0.5  x 1.1 ; >0.75  x 2 ; >0.95  x 10"""
+    import torch
+    s = scale.clone()
+    s = torch.where(acc_rate < 0.001, scale * 0.1, s)
+    s = torch.where((acc_rate >= 0.001) & (acc_rate < 0.05), scale * 0.5, s)
+    s = torch.where((acc_rate >= 0.05) & (acc_rate < 0.2), scale * 0.9, s)
+    s = torch.where(acc_rate > 0.95, scale * 10.0, s)
+    s = torch.where((acc_rate > 0.75) & (acc_rate <= 0.95), scale * 2.0, s)
+    s = torch.where((acc_rate > 0.5) & (acc_rate <= 0.75), scale * 1.1, s)
+    return s
+
+
+def calc_beta(likelihoods, beta, coef_variation=1.0):
+    """Next tempering beta + importance weights by bisection (beat/sampler/smc.py:133-165), numpy on [n_chains]."""
+    likelihoods = np.asarray(likelihoods, dtype=np.float64)
+    low_beta, up_beta, old_beta = beta, 2.0, beta
+    lmax = likelihoods.max()
+    while up_beta - low_beta > 1e-6:
+        current_beta = (low_beta + up_beta) / 2.0
+        temp = np.exp((current_beta - beta) * (likelihoods - lmax))
+        cov_temp = np.std(temp) / np.mean(temp)
+        if cov_temp > coef_variation:
+            up_beta = current_beta
+        else:
+            low_beta = current_beta
+    return current_beta, old_beta, temp / np.sum(temp)
+
+
+def ensure_cov_psd(cov):
+    """beat/utility.py:1034-1056: symmetrise / repair a covariance that is not positive definite."""
+    try:
+        np.linalg.cholesky(cov)
+        return cov
+    except np.linalg.LinAlgError:
+        w, v = np.linalg.eigh((cov + cov.T) / 2.0)
+        w = np.clip(w, 1e-12 * max(1.0, w.max()), None)
+        return (v * w).dot(v.T)
+
+
+def calc_covariance(array_population, weights):
+    """Weighted sample covariance of the population (beat/sampler/smc.py:167-186)."""
+    cov = np.cov(array_population, aweights=np.asarray(weights).ravel(), bias=False, rowvar=0)
+    cov = ensure_cov_psd(np.atleast_2d(cov))
+    if np.isnan(cov).any() or np.isinf(cov).any():
+        raise ValueError("Sample covariances contains Inf or NaN! Please try reducing the upper and lower bounds of hyper parameters!")
+    return cov
+
+
+def resample(weights, rng):
+    """Kitagawa's deterministic resampling (beat/sampler/smc.py:290-324), vectorised: same output for the same u."""
+    n = len(weights)
+    cum_dist = np.cumsum(weights)
+    u = (np.arange(n) + rng.random()) / n
+    j = np.searchsorted(cum_dist, u, side="left")      # first j with cum_dist[j] >= u  <=>  `while u > cum_dist[j]: j += 1`
+    j = np.minimum(j, n - 1)
+    n_childs = np.bincount(j, minlength=n)
+    return np.repeat(np.arange(n), n_childs)
+
+
+class BatchedMetropolis:
+    """All chains of one rank advanced in lock-step.  ``evaluator(q_dev) -> (logpts, like)`` on torch tensors."""
+
+    def __init__(self, evaluator, lower, upper, n_chains, device=None, scale=1.0, tune=True, tune_interval=100, seed=0):
+        import torch
+        self.torch = torch
+        self.evaluator = evaluator
+        self.device = device if device is not None else torch.device("cpu")
+        self.lower = torch.as_tensor(np.asarray(lower, dtype=np.float64), device=self.device)
+        self.upper = torch.as_tensor(np.asarray(upper, dtype=np.float64), device=self.device)
+        self.n_chains = n_chains
+        self.n_params = self.lower.numel()
+        self.scaling = torch.full((n_chains,), float(scale), dtype=torch.float64, device=self.device)
+        self.tune, self.tune_interval = tune, tune_interval
+        self.steps_until_tune = tune_interval
+        self.accepted = torch.zeros(n_chains, dtype=torch.float64, device=self.device)
+        self.gen = torch.Generator(device=self.device)
+        self.gen.manual_seed(int(seed))
+        self.beta = 1.0
+        self.n_evals = 0
+        self.chol = None
+
+    def set_proposal_covariance(self, cov):
+        """MultivariateNormal proposal (sampler/base.py:163-167): draws = z @ chol(cov).T."""
+        L = np.linalg.cholesky(ensure_cov_psd(np.atleast_2d(cov)))
+        self.chol = self.torch.as_tensor(L, device=self.device)
+
+    def initial_llk(self, q):
+        """Stage 0: evaluate the start population; non-finite llk raises (metropolis.py:277-284)."""
+        logpts, like = self.evaluator(q)
+        self.n_evals += q.shape[0]
+        if not bool(self.torch.isfinite(like).all()):
+            raise ValueError("Got NaN in likelihood evaluation! Invalid model definition? Or starting point outside prior bounds!")
+        return logpts, like
+
+    def step(self, q0, logpts0, like0):
+        """One lock-step Metropolis step for every chain.  Returns (q_new, logpts_new, like_new, accepted_mask)."""
+        torch = self.torch
+        if self.tune and self.steps_until_tune == 0:
+            self.scaling = tune_scale(self.scaling, self.accepted / float(self.tune_interval))
+            self.steps_until_tune = self.tune_interval
+            self.accepted.zero_()
+        z = torch.randn((self.n_chains, self.n_params), dtype=torch.float64, device=self.device, generator=self.gen)
+        delta = (z @ self.chol.T) * self.scaling[:, None]
+        q = q0 + delta
+        inside = ((q >= self.lower) & (q <= self.upper)).all(dim=1)
+        # out-of-prior proposals are rejected without being trusted: evaluate a safe copy (the previous point) there
+        q_eval = torch.where(inside[:, None], q, q0).contiguous()
+        logpts, like = self.evaluator(q_eval)
+        self.n_evals += int(inside.sum())
+        log_u = torch.log(torch.rand(self.n_chains, dtype=torch.float64, device=self.device, generator=self.gen))
+        ratio = self.beta * (like - like0)
+        accept = inside & torch.isfinite(ratio) & (log_u < ratio)          # pymc metrop_select
+        q_new = torch.where(accept[:, None], q, q0)
+        logpts_new = torch.where(accept[:, None], logpts, logpts0)
+        like_new = torch.where(accept, like, like0)
+        self.accepted += accept.to(torch.float64)
+        self.steps_until_tune -= 1
+        return q_new, logpts_new, like_new, accept
+
+
+def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_variation=1.0, tune_interval=None, seed=0,
+               sample_factor_final_stage=1, max_stages=200, initial_population=None, update_weights=None, log=None):
+    """Batched restatement of ``smc_sample``'s stage loop (beat/sampler/smc.py:459-546).
+
+    Returns dict(population [n_chains, n_params], likelihoods [n_chains], logpts, betas, n_evals, acceptance).
+    ``update_weights(map_point) -> None`` mirrors the ``update`` hook (smc.py:492-503): called with the MAP end
+    point after each stage; the caller re-uploads weights (``BatchedFFILogLike.update_weights``) and the end points
+    are re-evaluated."""
+    import torch
+    from . import distributed as D
+    device = device if device is not None else torch.device("cpu")
+    rng = np.random.default_rng(seed)
+    lower = np.asarray(lower, dtype=np.float64)
+    upper = np.asarray(upper, dtype=np.float64)
+    n_params = lower.size
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    lo, hi = D.shard_range(n_chains, rank, world)
+    n_local = hi - lo
+    mh = BatchedMetropolis(evaluator, lower, upper, n_local, device=device, tune=True,
+                           tune_interval=tune_interval or max(1, n_steps // 4 or 1), seed=seed * 7919 + rank)
+
+    # stage 0: population from the prior (metropolis.py:128-152), identical on all ranks (shared seed)
+    if initial_population is None:
+        pop = rng.uniform(lower, upper, (n_chains, n_params))
+    else:
+        pop = np.array(initial_population, dtype=np.float64, copy=True)
+    q = torch.as_tensor(pop[lo:hi], device=device).contiguous()
+    logpts, like = mh.initial_llk(q)
+
+    beta, betas, stage = 0.0, [0.0], 0
+    acc_hist = []
+    while beta < 1.0 and stage < max_stages:
+        like_all = D.allgather_chains(like).cpu().numpy()                    # THE per-stage exchange
+        q_all = D.allgather_chains(q).cpu().numpy()
+        logpts_all = D.allgather_chains(logpts)
+        if update_weights is not None:
+            update_weights(q_all[int(np.argmax(like_all))])
+            logpts, like = mh.initial_llk(q)
+            like_all = D.allgather_chains(like).cpu().numpy()
+            logpts_all = D.allgather_chains(logpts)
+        new_beta, old_beta, weights = calc_beta(like_all, beta, coef_variation)
+        final = new_beta > 1.0
+        if final:                                                            # smc.py:507-513,522-524
+            new_beta = 1.0
+            temp = np.exp((1.0 - old_beta) * (like_all - like_all.max()))
+            weights = temp / temp.sum()
+        cov = calc_covariance(q_all, weights)
+        idx = resample(weights, rng)                                         # identical on all ranks (shared rng)
+        mh.set_proposal_covariance(cov)
+        mh.beta = new_beta
+        sel = torch.as_tensor(idx[lo:hi], device=device)
+        q = torch.as_tensor(q_all, device=device)[sel].contiguous()
+        like = torch.as_tensor(like_all, device=device)[sel].contiguous()
+        logpts = logpts_all[sel].contiguous()
+        draws = n_steps * (sample_factor_final_stage if final else 1)
+        mh.steps_until_tune = mh.tune_interval
+        mh.accepted.zero_()
+        n_acc = 0.0
+        for _ in range(draws):
+            q, logpts, like, acc = mh.step(q, logpts, like)
+            n_acc += float(acc.double().mean())
+        acc_hist.append(n_acc / max(1, draws))
+        beta = new_beta
+        betas.append(beta)
+        stage += 1
+        if log:
+            log("stage %d beta %.6f acceptance %.3f" % (stage, beta, acc_hist[-1]))
+    like_all = D.allgather_chains(like).cpu().numpy()
+    q_all = D.allgather_chains(q).cpu().numpy()
+    logpts_all = D.allgather_chains(logpts).cpu().numpy()
+    n_evals = torch.tensor([mh.n_evals], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(n_evals)
+    return dict(population=q_all, likelihoods=like_all, logpts=logpts_all, betas=betas, n_stages=stage,
+                n_evals=int(n_evals.item()), acceptance=acc_hist)

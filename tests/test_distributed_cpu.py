@@ -1,0 +1,70 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: contiguous chain shards + one all-gather of llk reproduce
+the single-process population exactly."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_eval(q):
+    """Stand-in evaluator with the engine's return convention (logpts [B, n_out], like [B])."""
+    logpts = torch.stack([-(q ** 2).sum(dim=1), -q.abs().sum(dim=1), q[:, 0] * 0.5], dim=1)
+    return logpts, logpts.sum(dim=1)
+
+
+def _worker(rank, world, port, n_chains, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from beat_b200 import distributed as D
+    r, w = D.init_process_group(backend="gloo")
+    assert (r, w) == (rank, world)
+    rng = np.random.default_rng(7)
+    Q = torch.from_numpy(rng.standard_normal((n_chains, 11)))           # replicated population
+    pop = D.ShardedPopulation(n_chains, _fake_eval)
+    q_local = pop.local(Q)
+    assert q_local.shape[0] == n_chains // world
+    logpts_local, like_local = pop.evaluate(q_local)
+    like_all = pop.gather_llk(like_local)
+    Q_all = pop.gather_population(q_local)
+    torch.save({"like": like_all, "Q": Q_all, "lo": pop.lo, "hi": pop.hi}, os.path.join(out_dir, "r%d.pt" % rank))
+    with pytest.raises(ValueError):
+        D.shard_range(n_chains + 1, rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_population_matches_single_process(tmp_path, world):
+    n_chains = 12
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_chains, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(7)
+    Q = torch.from_numpy(rng.standard_normal((n_chains, 11)))
+    _, like_ref = _fake_eval(Q)
+    for r in range(world):
+        got = torch.load(os.path.join(str(tmp_path), "r%d.pt" % r))
+        assert torch.equal(got["like"], like_ref)
+        assert torch.equal(got["Q"], Q)
+        assert (got["lo"], got["hi"]) == (r * n_chains // world, (r + 1) * n_chains // world)
+
+
+def test_shard_range_contract():
+    from beat_b200.distributed import shard_range
+    assert [shard_range(4000, r, 8) for r in (0, 7)] == [(0, 500), (3500, 4000)]
+    with pytest.raises(ValueError, match="whole number"):
+        shard_range(10, 0, 4)
