@@ -104,6 +104,11 @@ struct beatgpu_ctx {
     size_t tmp_bytes[6] = {0, 0, 0, 0, 0, 0};
     // accounting
     long long n_launches = 0;
+    bool persistent = false;        // BEATGPU_PERSISTENT=1: fused kernel with one resident CTA wave walking the items
+    int stack_mode = 1;             // 0 = fused kernel (CTA per target x chain), 1 = patch-chunked warps + misfit pass
+    int chunk_patches = 32;         // BEATGPU_CHUNK: target patches per chunk (<= 32)
+    double* d_partial = nullptr;    // [B, nt, nchunk, ns] scratch of the chunked path
+    size_t partial_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
 };
@@ -234,7 +239,13 @@ int launch_stack_nvar(beatgpu_ctx* ctx, const StackArgs& a)
     do {                                                                                                             \
         if (smem > 48 * 1024)                                                                                        \
             CK(cudaFuncSetAttribute(gf_stack_misfit_kernel<T, K, NV, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        gf_stack_misfit_kernel<T, K, NV, WS><<<(unsigned)grid, kStackThreads, smem, ctx->stream>>>(a);              \
+        long g = grid;                                                                                               \
+        if (ctx->persistent) {                                                                                       \
+            int per_sm = 0;                                                                                          \
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gf_stack_misfit_kernel<T, K, NV, WS>, kStackThreads, smem)); \
+            g = std::min<long>(grid, (long)std::max(1, per_sm) * ctx->prop.multiProcessorCount);                     \
+        }                                                                                                            \
+        gf_stack_misfit_kernel<T, K, NV, WS><<<(unsigned)g, kStackThreads, smem, ctx->stream>>>(a);                 \
     } while (0)
     switch (a.nvar) {
         case 1: LAUNCH(1); break;
@@ -256,6 +267,59 @@ int launch_stack(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
     } else {
         return (w.interp == BEATGPU_NEAREST) ? launch_stack_nvar<double, 1, WS>(ctx, a) : launch_stack_nvar<double, 4, WS>(ctx, a);
     }
+}
+
+template <typename T, int K>
+int launch_chunk_nvar(beatgpu_ctx* ctx, const ChunkArgs& ca)
+{
+    const long n_items = (long)ca.s.nt * ca.nchunk * ca.s.B;
+    const long grid = (n_items + kChunkWarps - 1) / kChunkWarps;
+    if (grid > 2147483647L) return fail(ctx, BEATGPU_E_ARG, "grid too large: %ld", grid);
+    switch (ca.s.nvar) {
+        case 1: gf_stack_chunk_kernel<T, K, 1><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); break;
+        case 2: gf_stack_chunk_kernel<T, K, 2><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); break;
+        case 3: gf_stack_chunk_kernel<T, K, 3><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); break;
+        default: return fail(ctx, BEATGPU_E_ARG, "n_slipvars must be 1..3, got %d", ca.s.nvar);
+    }
+    CKL();
+    return BEATGPU_OK;
+}
+
+// chunked path: partial synthetics per (chain, target, patch chunk), then residual + misfit
+int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
+{
+    ChunkArgs ca;
+    ca.s = a;
+    const int nch0 = (a.np + ctx->chunk_patches - 1) / ctx->chunk_patches;
+    ca.chunk = (a.np + nch0 - 1) / nch0;                 // balanced chunks
+    ca.nchunk = (a.np + ca.chunk - 1) / ca.chunk;
+    const size_t need = (size_t)a.B * a.nt * ca.nchunk * a.ns * sizeof(double);
+    if (ctx->partial_bytes < need) {
+        if (ctx->d_partial) cudaFree(ctx->d_partial);
+        ctx->d_partial = nullptr; ctx->partial_bytes = 0;
+        CK(cudaMalloc((void**)&ctx->d_partial, need));
+        ctx->partial_bytes = need;
+    }
+    ca.partial = ctx->d_partial;
+    int rc;
+    if (w.store_dtype == BEATGPU_F32)
+        rc = (w.interp == BEATGPU_NEAREST) ? launch_chunk_nvar<float, 1>(ctx, ca) : launch_chunk_nvar<float, 4>(ctx, ca);
+    else
+        rc = (w.interp == BEATGPU_NEAREST) ? launch_chunk_nvar<double, 1>(ctx, ca) : launch_chunk_nvar<double, 4>(ctx, ca);
+    if (rc) return rc;
+    MisfitArgs m;
+    memset(&m, 0, sizeof(m));
+    m.B = a.B; m.nt = a.nt; m.ns = a.ns;
+    m.resid = nullptr; m.partial = ctx->d_partial; m.nchunk = ca.nchunk; m.data = a.data; m.chain_bad = a.chain_bad;
+    m.hyp = a.hyp; m.hyp_sc = a.hyp_sc; m.hyper_idx = a.hyper_idx;
+    m.misfit_mode = a.misfit_mode; m.bw = a.bw; m.dense_upper = a.dense_upper;
+    m.W = a.W; m.slog_pdet = a.slog_pdet; m.nsamp = a.nsamp;
+    m.logpts = a.logpts; m.logpts_sc = a.logpts_sc; m.out_ofs = a.out_ofs;
+    const size_t smem = (size_t)a.ns * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    misfit_kernel<<<(unsigned)((long)a.nt * a.B), kStackThreads, smem, ctx->stream>>>(m);
+    CKL();
+    return BEATGPU_OK;
 }
 
 void fill_static(const WaveMap& w, StackArgs& a, int nvar)
@@ -351,6 +415,9 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
         fprintf(stderr, "libbeatgpu: warning: built for sm_100a, device is sm_%d%d\n", c->prop.major, c->prop.minor);
     for (int v = 0; v < BEATGPU_MAX_SLIPVARS; ++v) c->canon_slip[v] = 0;
     memset(&c->layout, 0, sizeof(c->layout));
+    if (const char* e = getenv("BEATGPU_PERSISTENT")) c->persistent = atoi(e) != 0;
+    if (const char* e = getenv("BEATGPU_STACK_MODE")) c->stack_mode = (strcmp(e, "fused") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
+    if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) c->chunk_patches = v; }
     (void)ctx;
     *out = c;
     return BEATGPU_OK;
@@ -374,6 +441,7 @@ void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
     cudaFree(ctx->d_nd); cudaFree(ctx->d_ns); cudaFree(ctx->d_pofs); cudaFree(ctx->d_psize); cudaFree(ctx->d_fixed);
     cudaFree(ctx->d_q); cudaFree(ctx->d_logpts); cudaFree(ctx->d_like); cudaFree(ctx->d_t0); cudaFree(ctx->d_bad);
     cudaFree(ctx->d_viol);
+    cudaFree(ctx->d_partial);
     for (int i = 0; i < 6; ++i) cudaFree(ctx->d_tmp[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -891,7 +959,11 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
             a.hyp = hyp.p; a.hyp_sc = hyp.stride;
             a.logpts = logpts; a.logpts_sc = n_out; a.out_ofs = w.out_ofs;
             a.synth = nullptr; a.chain_bad = ctx->d_bad; a.violations = ctx->d_viol;
-            if ((rc = launch_stack<false>(ctx, w, a))) return rc;
+            // the chunked path needs a scratch of B*nt*nchunk*ns doubles; fall back to the fused kernel beyond 8 GiB
+            const size_t nchunk_est = (size_t)(ctx->np_total + ctx->chunk_patches - 1) / ctx->chunk_patches + 1;
+            const bool chunked = ctx->stack_mode == 1 && ctx->np_total > ctx->chunk_patches &&
+                                 (size_t)B * w.nt * nchunk_est * w.ns * sizeof(double) <= ((size_t)8 << 30);
+            if ((rc = chunked ? launch_stack_chunked(ctx, w, a) : launch_stack<false>(ctx, w, a))) return rc;
         }
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         ctx->ev_valid = true;

@@ -64,10 +64,11 @@ struct StackArgs {
     unsigned long long* violations;
 };
 
-template <int K, int NVAR>
+// WT = float for f32 libraries (weights are rounded once, like the library values themselves), double for f64.
+template <typename WT, int K, int NVAR>
 struct __align__(16) PatchPlan {
     int row[4];                // library row index of each tap (already moved onto a valid row when its weight is zero)
-    double w[K * NVAR];        // weight of tap k, slip variable v at w[v*K + k]
+    WT w[K * NVAR];            // weight of tap k, slip variable v at w[v*K + k]
 };
 
 // sample index (within the window) of element e (0..3) held by vector slot j
@@ -80,7 +81,7 @@ template <typename T, int K, int NVAR, bool WRITE_SYNTH>
 __global__ void __launch_bounds__(kStackThreads)
 gf_stack_misfit_kernel(StackArgs a)
 {
-    using Plan = PatchPlan<K, NVAR>;
+    using Plan = PatchPlan<T, K, NVAR>;
     __shared__ Plan plan[kPlanChunk];
     __shared__ double red[kStackWarps][kWindow];
     __shared__ double red_q[kStackWarps];
@@ -90,9 +91,16 @@ gf_stack_misfit_kernel(StackArgs a)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int c = blockIdx.x % a.B;
-    const int t = blockIdx.x / a.B;
+    // Persistent CTAs: the grid is sized to the number of co-resident CTAs and every CTA walks the (target, chain)
+    // items with stride gridDim.  All CTAs start together and every item costs the same, so at any moment the
+    // resident CTAs are at (nearly) the same patch of the same target: the rows they gather come from a working
+    // set of a few (t, p) blocks (~1 MB each) that stays in L2, instead of being spread over the whole target.
+    const long n_items = (long)a.nt * a.B;
+    for (long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int c = (int)(item % a.B);
+    const int t = (int)(item / a.B);
 
+    __syncthreads();                                         // previous item fully retired (shared memory reuse)
     if (tid == 0) s_bad = (a.chain_bad && a.chain_bad[c]) ? 1 : 0;
 
     const double* dur = a.dur + (long)c * a.dur_sc;
@@ -123,7 +131,7 @@ gf_stack_misfit_kernel(StackArgs a)
                     viol = (x != x) || (y != y) || (di < 0) || (di >= a.ndur) || (si < 0) || (si >= a.nst);
                     pl.row[0] = viol ? 0 : (int)(base + (long)di * a.nst + si);
 #pragma unroll
-                    for (int v = 0; v < NVAR; ++v) pl.w[v] = a.slip[v][(long)c * a.slip_sc[v] + p];
+                    for (int v = 0; v < NVAR; ++v) pl.w[v] = (T)a.slip[v][(long)c * a.slip_sc[v] + p];
                 } else {                                                                 // multilinear (base.py:513-517,560-564,662-679)
                     const int dc = (int)ceil(x);
                     const int sc = (int)ceil(y);
@@ -150,17 +158,17 @@ gf_stack_misfit_kernel(StackArgs a)
 #pragma unroll
                     for (int v = 0; v < NVAR; ++v) {
                         const double u = a.slip[v][(long)c * a.slip_sc[v] + p];
-                        pl.w[v * K + 0] = w_cc * u;
-                        pl.w[v * K + 1] = w_fc * u;
-                        pl.w[v * K + 2] = w_cf * u;
-                        pl.w[v * K + 3] = w_ff * u;
+                        pl.w[v * K + 0] = (T)(w_cc * u);
+                        pl.w[v * K + 1] = (T)(w_fc * u);
+                        pl.w[v * K + 2] = (T)(w_cf * u);
+                        pl.w[v * K + 3] = (T)(w_ff * u);
                     }
                 }
                 if (viol) {
                     if (s0 == 0) atomicAdd(a.violations, 1ULL);
                     s_bad = 1;
 #pragma unroll
-                    for (int q = 0; q < K * NVAR; ++q) pl.w[q] = 0.0;
+                    for (int q = 0; q < K * NVAR; ++q) pl.w[q] = (T)0;
                 }
                 plan[i] = pl;
             }
@@ -185,19 +193,26 @@ gf_stack_misfit_kernel(StackArgs a)
                                 g[u][v * K + k] = ld_on ? __ldg(reinterpret_cast<const float4*>(row) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
                             }
                     }
+                    // f32 library: products and the 2*K*NVAR-term partial sum in f32 (FFMA pipe), one f32->f64
+                    // conversion per element per patch pair; the running sum over patches stays f64.
+                    float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
                         if (u == 1 && !has2) break;
                         const int ii = (u == 0) ? i : i2;
 #pragma unroll
                         for (int q = 0; q < K * NVAR; ++q) {
-                            const double w = plan[ii].w[q];
-                            acc[0] = fma(w, (double)g[u][q].x, acc[0]);
-                            acc[1] = fma(w, (double)g[u][q].y, acc[1]);
-                            acc[2] = fma(w, (double)g[u][q].z, acc[2]);
-                            acc[3] = fma(w, (double)g[u][q].w, acc[3]);
+                            const float w = plan[ii].w[q];
+                            part.x = fmaf(w, g[u][q].x, part.x);
+                            part.y = fmaf(w, g[u][q].y, part.y);
+                            part.z = fmaf(w, g[u][q].z, part.z);
+                            part.w = fmaf(w, g[u][q].w, part.w);
                         }
                     }
+                    acc[0] += (double)part.x;
+                    acc[1] += (double)part.y;
+                    acc[2] += (double)part.z;
+                    acc[3] += (double)part.w;
                 }
             } else {
                 // f64 storage: a window of 128 samples = 64 16-byte vectors; lane reads vectors `lane` and `lane+32`
@@ -246,7 +261,7 @@ gf_stack_misfit_kernel(StackArgs a)
 
     if (WRITE_SYNTH) {
         if (s_bad) for (int k = tid; k < a.ns; k += kStackThreads) a.synth[((long)c * a.nt + t) * a.ns + k] = CUDART_NAN;
-        return;
+        continue;
     }
 
     // ---------------- (4) misfit: quad = |U r|^2  (distributions.py:128,136) ----------------
@@ -286,6 +301,7 @@ gf_stack_misfit_kernel(StackArgs a)
         if (s_bad) lp = CUDART_NAN;
         a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = lp;
     }
+    }   // item loop
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -293,7 +309,10 @@ gf_stack_misfit_kernel(StackArgs a)
 // ---------------------------------------------------------------------------------------------------------
 struct MisfitArgs {
     int B, nt, ns;
-    const double* resid;                  // [B, nt, ns]
+    const double* resid;                  // [B, nt, ns]  (explicit residuals), or nullptr when `partial` is given
+    const double* partial; int nchunk;    // [B, nt, nchunk, ns] partial synthetics of gf_stack_chunk_kernel
+    const double* data;                   // [nt, ns] (with `partial`)
+    const unsigned char* chain_bad;       // optional [B]
     const double* hyp; long hyp_sc; const int* hyper_idx;
     int misfit_mode; int bw; int dense_upper;
     const double* W; const double* slog_pdet; const int* nsamp;
@@ -307,8 +326,18 @@ __global__ void __launch_bounds__(kStackThreads) misfit_kernel(MisfitArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c = blockIdx.x % a.B, t = blockIdx.x / a.B;
     const int ns = a.ns;
-    const double* r = a.resid + ((long)c * a.nt + t) * ns;
-    for (int k = tid; k < ns; k += kStackThreads) resid[k] = r[k];
+    if (a.partial) {
+        // synth = sum of the patch-chunk partials in fixed chunk order (deterministic); residual = data - synth
+        const double* pp = a.partial + ((long)c * a.nt + t) * a.nchunk * ns;
+        for (int k = tid; k < ns; k += kStackThreads) {
+            double s = pp[k];
+            for (int j = 1; j < a.nchunk; ++j) s += pp[(long)j * ns + k];
+            resid[k] = a.data[(long)t * ns + k] - s;                                     // seismic.py:1332
+        }
+    } else {
+        const double* r = a.resid + ((long)c * a.nt + t) * ns;
+        for (int k = tid; k < ns; k += kStackThreads) resid[k] = r[k];
+    }
     __syncthreads();
     double q = 0.0;
     if (a.misfit_mode == MISFIT_DIAG) {
@@ -340,7 +369,188 @@ __global__ void __launch_bounds__(kStackThreads) misfit_kernel(MisfitArgs a)
         const double hp = a.hyp[(long)c * a.hyp_sc + a.hyper_idx[t]];
         const double M = (double)(short)a.nsamp[t];
         const double norm = M * (2.0 * hp + 1.8378770664093453);
-        a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = (-0.5) * (a.slog_pdet[t] + norm + (1.0 / exp(hp * 2.0)) * quad);
+        double lp = (-0.5) * (a.slog_pdet[t] + norm + (1.0 / exp(hp * 2.0)) * quad);
+        if (a.chain_bad && a.chain_bad[c]) lp = CUDART_NAN;
+        a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = lp;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Patch-chunked stacking: one WARP per (target, patch-chunk, chain) item, items ordered (t, chunk, c) so that all
+// warps resident at a time gather from the same few (t, p) library blocks (chunk * nvar * ndur*nst*ld*sizeof(T)
+// bytes, ~26 MB at C3 with 25-patch chunks) which therefore stay in L2 while every chain streams through them:
+// HBM traffic tends to one pass over the touched library instead of one pass per ~wave of chains.  No block-level
+// barrier at all (plan, stream, store are warp-private).  Partial synthetics go to a [B, nt, nchunk, ns] f64
+// scratch; misfit_kernel sums them in chunk order and finishes residual + misfit.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kChunkMax = 32;            // patches per chunk (one lane plans one patch)
+constexpr int kChunkWarps = 4;
+
+struct ChunkArgs {
+    StackArgs s;                          // library, axes and per-chain inputs as for the fused kernel
+    int chunk;                            // patches per chunk (<= kChunkMax)
+    int nchunk;
+    double* partial;                      // [B, nt, nchunk, ns]
+};
+
+template <typename T, int K, int NVAR>
+__global__ void __launch_bounds__(kChunkWarps * 32)
+gf_stack_chunk_kernel(ChunkArgs ca)
+{
+    using Plan = PatchPlan<T, K, NVAR>;
+    __shared__ Plan plan_s[kChunkWarps][kChunkMax];
+    const StackArgs& a = ca.s;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long n_items = (long)a.nt * ca.nchunk * a.B;
+    const long item = (long)blockIdx.x * kChunkWarps + warp;
+    if (item >= n_items) return;
+    const int c = (int)(item % a.B);
+    const int kc = (int)((item / a.B) % ca.nchunk);
+    const int t = (int)(item / ((long)a.B * ca.nchunk));
+    Plan* plan = plan_s[warp];
+
+    const int p0 = kc * ca.chunk;
+    const int pn = min(ca.chunk, a.np - p0);
+    const double* dur = a.dur + (long)c * a.dur_sc;
+    const double* st = a.st + (long)c * a.st_sc + (long)t * a.st_st;
+    double corr = 0.0;
+    if (a.corr) corr = a.corr[(long)c * a.corr_sc + a.station_idx[t]];
+    const long rows_per_patch = (long)a.ndur * a.nst;
+
+    // ---- plan (one lane per patch; same arithmetic as the fused kernel / ffi/base.py:506-517,553-564,676-679)
+    bool viol = false;
+    if (lane < pn) {
+        const int p = p0 + lane;
+        const double x = (dur[p] - a.dur_min) / a.dur_step;
+        const double y = ((st[p] - corr) - a.st_min) / a.st_step;
+        const long base = ((long)t * a.np + p) * rows_per_patch;
+        Plan pl;
+        if (K == 1) {
+            const int di = (int)rint(x);
+            const int si = (int)rint(y);
+            viol = (x != x) || (y != y) || (di < 0) || (di >= a.ndur) || (si < 0) || (si >= a.nst);
+            pl.row[0] = viol ? 0 : (int)(base + (long)di * a.nst + si);
+            pl.row[1] = pl.row[2] = pl.row[3] = 0;
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) pl.w[v] = (T)a.slip[v][(long)c * a.slip_sc[v] + p];
+        } else {
+            const int dc = (int)ceil(x);
+            const int sc = (int)ceil(y);
+            const double rf = (double)dc - x;
+            const double sf = (double)sc - y;
+            const int dfl = (rf == 0.0) ? dc : dc - 1;
+            const int sfl = (sf == 0.0) ? sc : sc - 1;
+            viol = (x != x) || (y != y) || (dc < 0) || (dc >= a.ndur) || (dfl < 0) || (sc < 0) || (sc >= a.nst) || (sfl < 0);
+            if (viol) {
+                pl.row[0] = pl.row[1] = pl.row[2] = pl.row[3] = 0;
+            } else {
+                pl.row[0] = (int)(base + (long)dc * a.nst + sc);
+                pl.row[1] = (int)(base + (long)dc * a.nst + sfl);
+                pl.row[2] = (int)(base + (long)dfl * a.nst + sc);
+                pl.row[3] = (int)(base + (long)dfl * a.nst + sfl);
+            }
+            const double w_cc = (1.0 - sf) * (1.0 - rf);
+            const double w_fc = sf * (1.0 - rf);
+            const double w_cf = (1.0 - sf) * rf;
+            const double w_ff = sf * rf;
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                const double u = a.slip[v][(long)c * a.slip_sc[v] + p];
+                pl.w[v * K + 0] = (T)(w_cc * u);
+                pl.w[v * K + 1] = (T)(w_fc * u);
+                pl.w[v * K + 2] = (T)(w_cf * u);
+                pl.w[v * K + 3] = (T)(w_ff * u);
+            }
+        }
+        if (viol) {
+            atomicAdd(a.violations, 1ULL);
+#pragma unroll
+            for (int q = 0; q < K * NVAR; ++q) pl.w[q] = (T)0;
+        }
+        plan[lane] = pl;
+    }
+    const bool any_viol = __any_sync(0xffffffffu, viol);
+    __syncwarp();
+
+    double* out = ca.partial + (((long)c * a.nt + t) * ca.nchunk + kc) * a.ns;
+    for (int s0 = 0; s0 < a.ns; s0 += kWindow) {
+        const int wlen = min(kWindow, a.ns - s0);
+        const int nvec = (wlen * (int)sizeof(T) + 15) / 16;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (sizeof(T) == 4) {
+            const bool active = lane < nvec;
+            for (int i = 0; i < pn; i += 2) {
+                const bool has2 = (i + 1) < pn;
+                float4 g[2][K * NVAR];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ii = (u == 0 || has2) ? i + u : i;
+                    const bool ld_on = active && (u == 0 || has2);
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+                        for (int k = 0; k < K; ++k) {
+                            const float* row = reinterpret_cast<const float*>(a.G[v]) + (long)plan[ii].row[k] * a.ld + s0;
+                            g[u][v * K + k] = ld_on ? __ldg(reinterpret_cast<const float4*>(row) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                }
+                float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (u == 1 && !has2) break;
+#pragma unroll
+                    for (int q = 0; q < K * NVAR; ++q) {
+                        const float w = plan[i + u].w[q];
+                        part.x = fmaf(w, g[u][q].x, part.x);
+                        part.y = fmaf(w, g[u][q].y, part.y);
+                        part.z = fmaf(w, g[u][q].z, part.z);
+                        part.w = fmaf(w, g[u][q].w, part.w);
+                    }
+                }
+                acc[0] += (double)part.x;
+                acc[1] += (double)part.y;
+                acc[2] += (double)part.z;
+                acc[3] += (double)part.w;
+            }
+        } else {
+            const bool act0 = lane < nvec, act1 = (lane + 32) < nvec;
+            for (int i = 0; i < pn; ++i) {
+                double2 g0[K * NVAR], g1[K * NVAR];
+#pragma unroll
+                for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+                    for (int k = 0; k < K; ++k) {
+                        const double* row = reinterpret_cast<const double*>(a.G[v]) + (long)plan[i].row[k] * a.ld + s0;
+                        g0[v * K + k] = act0 ? __ldg(reinterpret_cast<const double2*>(row) + lane) : make_double2(0.0, 0.0);
+                        g1[v * K + k] = act1 ? __ldg(reinterpret_cast<const double2*>(row) + lane + 32) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                for (int q = 0; q < K * NVAR; ++q) {
+                    const double w = plan[i].w[q];
+                    acc[0] = fma(w, g0[q].x, acc[0]);
+                    acc[1] = fma(w, g0[q].y, acc[1]);
+                    acc[2] = fma(w, g1[q].x, acc[2]);
+                    acc[3] = fma(w, g1[q].y, acc[3]);
+                }
+            }
+        }
+        if (any_viol) acc[0] = acc[1] = acc[2] = acc[3] = CUDART_NAN;
+        if ((a.ns & 1) == 0) {
+            // (e0,e1) and (e2,e3) are adjacent samples for both storage types: two 16-byte stores per lane
+#pragma unroll
+            for (int e = 0; e < 4; e += 2) {
+                const int sidx = slot_sample<T>(lane, e);
+                if (sidx + 1 < wlen) *reinterpret_cast<double2*>(out + s0 + sidx) = make_double2(acc[e], acc[e + 1]);
+                else if (sidx < wlen) out[s0 + sidx] = acc[e];
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int sidx = slot_sample<T>(lane, e);
+                if (sidx < wlen) out[s0 + sidx] = acc[e];
+            }
+        }
     }
 }
 

@@ -33,6 +33,48 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    print("[bench %7.1fs] %s" % (time.perf_counter() - _T0, msg), file=sys.stderr, flush=True)
+
+
+def usable_cores():
+    """Host threads this process may use, bounded by memory (each worker peaks at ~0.6 GB of numpy temporaries)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        import psutil
+        n = min(n, max(1, int(psutil.virtual_memory().available / 2**30 / 1.5)))
+    except Exception:
+        pass
+    return max(1, min(n, int(os.environ.get("BENCH_MAX_CORES", "64"))))
+
+
+def _worker_init():
+    """One BLAS/OpenMP thread per worker: the pool already uses every core (128 workers x 128 BLAS threads spin-wait
+    each other to a standstill otherwise)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def pool_map(fn, items, cores, timeout):
+    """Fork pool that raises instead of hanging when a worker dies (reference: beat/parallel.py:186-282)."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork"), initializer=_worker_init) as ex:
+        list(ex.map(fn, range(cores), timeout=timeout))       # warm the workers
+        t0 = time.perf_counter()
+        list(ex.map(fn, items, chunksize=max(1, len(items) // (4 * cores)), timeout=timeout))
+        return time.perf_counter() - t0
+
+
 METRIC = "forward+loglike evals/sec (FFI seismic 200-patch)"
 UNIT = "evals/s"
 
@@ -88,13 +130,14 @@ def build_cpu_problem(args):
     return prob
 
 
-def cpu_baseline(args, n_evals_per_core=6, cores=None):
+def cpu_baseline(args, n_evals_per_core=4, cores=None):
     """Times the reference-style CPU path; returns (dict for the JSON line, evals/s)."""
-    import multiprocessing as mp
     from beat_b200 import synthetic
     from oracle import ffi_oracle
     subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    cores = cores or os.cpu_count()
+    cores = cores or usable_cores()
+    _worker_init()
+    log("cpu baseline: building host problem (%d cores)" % cores)
     prob = build_cpu_problem(args)
     n = max(cores, n_evals_per_core * cores)
     Q = synthetic.draw_chains(prob, n, seed=999)
@@ -106,13 +149,10 @@ def cpu_baseline(args, n_evals_per_core=6, cores=None):
     for i in range(n1):
         _cpu_eval(i)
     one = n1 / (time.perf_counter() - t0)
+    log("cpu baseline: 1 core %.2f evals/s; fanning %d chains over %d cores" % (one, n, cores))
     # all cores, chains fanned out over a fork pool (reference: beat/parallel.py:186-282)
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_eval, range(cores))          # warm the workers
-        t0 = time.perf_counter()
-        pool.map(_cpu_eval, range(n), chunksize=max(1, n // (4 * cores)))
-        allc = n / (time.perf_counter() - t0)
+    allc = n / pool_map(_cpu_eval, list(range(n)), cores, timeout=240)
+    log("cpu baseline: %d cores %.2f evals/s" % (cores, allc))
     info = {"value": allc, "unit": UNIT, "cores": cores, "kind": "port",
             "value_1core": one,
             "sample": "%d chains of the same C3 shapes (host library with 2 duration nodes, f64), one chain per call: "
@@ -125,9 +165,12 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
+    for v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(v, "1")
+    cores = usable_cores()
     # K timed steps, each a bounded sample (cores*2 chains); W warm-up steps
     import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
     from beat_b200 import synthetic
     from oracle import ffi_oracle
     subprocess.call(["make", "-s", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
@@ -136,15 +179,14 @@ def run_reference_arm(args):
     Q = synthetic.draw_chains(prob, per_step * (args.steps + args.warmup), seed=999)
     have_ref = ffi_oracle.load_reference_ext() is not None
     _CPU.update(prob=prob, Q=Q, impl="ref" if have_ref else "port")
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork"), initializer=_worker_init) as pool:
         k = 0
         for _ in range(args.warmup):
-            pool.map(_cpu_eval, range(k, k + per_step))
+            list(pool.map(_cpu_eval, range(k, k + per_step), timeout=300))
             k += per_step
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_cpu_eval, range(k, k + per_step))
+            list(pool.map(_cpu_eval, range(k, k + per_step), timeout=300))
             k += per_step
         dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
@@ -209,33 +251,6 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-class _DevBuf:
-    def __init__(self, ptr, shape, typestr):
-        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
-def fill_library_on_device(ev, prob, torch, device, store):
-    """Generate the synthetic GF libraries straight into the HBM buffers owned by libbeatgpu."""
-    from beat_b200 import synthetic
-    for iw, wm in enumerate(prob["wavemaps"]):
-        dims = (wm["nt"], prob["npatches"], wm["ndur"], wm["nst"], wm["ns"])
-        for iv, v in enumerate(prob["slip_vars"]):
-            ptr, ld = ev.alloc_library(iw, iv, dims, wm["dur_min"], wm["dur_step"], wm["st_min"], wm["st_step"])
-            tdt = torch.float32 if store == "f32" else torch.float64
-            view = torch.as_tensor(_DevBuf(ptr, dims[:4] + (ld,), "<f4" if store == "f32" else "<f8"), device=device)
-            A = torch.from_numpy(wm["A"][v]).to(device)
-            k0 = torch.from_numpy(wm["k0"][v]).to(device)
-            tb = 2
-            for t0 in range(0, wm["nt"], tb):
-                blk = synthetic.library_block(A[t0:t0 + tb], k0[t0:t0 + tb], wm["ndur"], wm["nst"], wm["ns"], wm["st_step"],
-                                              prob["dt"], xp=torch, dtype=tdt)
-                view[t0:t0 + tb, :, :, :, :wm["ns"]] = blk
-                if ld > wm["ns"]:
-                    view[t0:t0 + tb, :, :, :, wm["ns"]:] = 0
-            del view
-    torch.cuda.synchronize(device)
-
-
 def run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -247,11 +262,16 @@ def run_gpu_arm(args):
     # CPU baseline first (fork pool before CUDA is initialised in this process), rank 0 at N=1 only
     cpu_info = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu_baseline:
-        cpu_info, _ = cpu_baseline(args)
+        try:
+            cpu_info, _ = cpu_baseline(args)
+        except Exception as e:                     # a reported baseline must never take the GPU measurement down
+            cpu_info = {"value": None, "unit": UNIT, "cores": usable_cores(), "kind": "port", "sample": "failed: %r" % (e,)}
+            log("cpu baseline failed: %r" % (e,))
 
     import torch
     import torch.distributed as dist
     from beat_b200 import synthetic
+    from beat_b200.devlib import fill_library_on_device
     from beat_b200.engine import BatchedFFILogLike
 
     if not torch.cuda.is_available():
@@ -267,7 +287,9 @@ def run_gpu_arm(args):
     prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, build_library=False, **a)
     ev = BatchedFFILogLike.from_problem(prob, device=local_rank, store_dtype="float32" if args.store == "f32" else "float64",
                                         upload_libraries=False)
+    log("filling %.1f GB of synthetic GF library in HBM" % (lib_bytes(a, args.store) / 1e9))
     fill_library_on_device(ev, prob, torch, device, args.store)
+    log("library ready")
 
     n_rot = 3
     Qs = [synthetic.draw_chains(prob, B, seed=4321 + 17 * rank + 1000 * r) for r in range(n_rot)]
@@ -305,6 +327,7 @@ def run_gpu_arm(args):
     if not torch.isfinite(like_dev).all():
         raise SystemExit("bench.py: non-finite llk in the synthetic chains")
 
+    log("first evaluation ok (stack kernel %.2f ms); timing" % ev.ctx.last_stack_ms())
     # ---------------- value: inputs resident in HBM
     for i in range(args.warmup):
         step_resident(i)
@@ -333,6 +356,7 @@ def run_gpu_arm(args):
     ms_total = float(t.item())
     value = n_gpus * B * args.steps / (ms_total / 1e3)
 
+    log("value %.0f evals/s (%.2f ms/step)" % (value, ms_total / args.steps))
     # ---------------- e2e: host buffers through the C-ABI host entry
     for i in range(max(1, args.warmup // 2)):
         step_e2e(i)

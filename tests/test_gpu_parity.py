@@ -319,3 +319,65 @@ def test_device_resident_entry_matches_host_entry():
     assert np.array_equal(like.cpu().numpy(), host_like)
     assert ev.ctx.last_stack_ms() > 0
     ev.close()
+
+
+def test_near_map_accuracy_f32_storage():
+    """The hard regime for f32 libraries: chains close to the data-generating model, where the residual is a small
+    difference of large synthetics.  logpts must still match the f64 oracle to the north-star rtol 1e-5."""
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=6, subfaults=((6, 10, 2.0),), ns=64, ndur=6, seed=77)
+    q_true = synthetic.draw_chains(prob, 1, seed=8)[0]
+    _, synths, _ = O.ffi_seismic_eval(prob, synthetic.split_point(prob, q_true), impl="port", return_synth=True)
+    rng = np.random.default_rng(4)
+    wm = prob["wavemaps"][0]
+    sigma = 0.05 * np.abs(synths[0]).max(axis=1)
+    from beat_b200.covariance import Covariance, exponential_data_covariance
+    for t in range(wm["nt"]):
+        C = exponential_data_covariance(wm["ns"], 0.5, 2.0) * sigma[t] ** 2
+        cov = Covariance(data=C)
+        wm["U"][t], wm["slog_pdet"][t] = cov.chol_inverse, cov.log_pdet
+        wm["data"][t] = synths[0][t] + np.linalg.cholesky(C).dot(rng.standard_normal(wm["ns"]))
+    B = 64
+    Q = np.tile(q_true, (B, 1))
+    for name in prob["slip_vars"]:
+        o = prob["offsets"][name]
+        Q[1:, o:o + prob["npatches"]] += rng.normal(0, 0.01, (B - 1, prob["npatches"]))   # small slip perturbations
+    ref = _oracle_logpts(prob, Q)
+    for store, rtol in (("float64", 1e-10), ("float32", 1e-5)):
+        ev = BatchedFFILogLike.from_problem(prob, store_dtype=store)
+        logpts, like = ev(Q)
+        np.testing.assert_allclose(logpts, ref, rtol=rtol)
+        np.testing.assert_allclose(like, ref.sum(axis=1), rtol=rtol)
+        ev.close()
+
+
+@pytest.mark.parametrize("env", [
+    {"BEATGPU_STACK_MODE": "fused", "BEATGPU_PERSISTENT": "0"},
+    {"BEATGPU_STACK_MODE": "fused", "BEATGPU_PERSISTENT": "1"},
+    {"BEATGPU_STACK_MODE": "chunked", "BEATGPU_CHUNK": "7"},
+    {"BEATGPU_STACK_MODE": "chunked", "BEATGPU_CHUNK": "32"},
+])
+@pytest.mark.parametrize("case", ["ml_exp", "nn_exp", "station_corr_hp_specific", "two_subfaults", "long_traces", "odd_ns", "ml_dense"])
+def test_stack_execution_modes_vs_oracle(env, case, monkeypatch):
+    """Every scheduling variant of the stacking kernel (one CTA per item, persistent CTAs, patch-chunked warps with a
+    separate misfit pass) must give the oracle's answer; violations surface as IndexError in all of them."""
+    from beat_b200.engine import BatchedFFILogLike
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    args = dict(nt=4, subfaults=((5, 9, 2.0),), ns=32, ndur=4, seed=300 + sorted(CASES).index(case))
+    args.update(CASES[case])
+    prob = synthetic.make_problem(**args)
+    Q = synthetic.draw_chains(prob, 20, seed=15)
+    ref = _oracle_logpts(prob, Q)
+    for store, rtol in (("float64", 1e-10), ("float32", 1e-5)):
+        ev = BatchedFFILogLike.from_problem(prob, store_dtype=store)
+        logpts, like = ev(Q)
+        np.testing.assert_allclose(logpts, ref, rtol=rtol)
+        np.testing.assert_allclose(like, ref.sum(axis=1), rtol=rtol)
+        Qbad = Q.copy()
+        Qbad[5, prob["offsets"]["time"]] = 1e4
+        with pytest.raises(IndexError):
+            ev(Qbad)
+        got, _ = ev(Q)
+        assert np.array_equal(got, logpts)
+        ev.close()
