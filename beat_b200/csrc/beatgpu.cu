@@ -898,6 +898,46 @@ int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* res
     return BEATGPU_OK;
 }
 
+// rupture onset times for all chains / subfaults into ctx->d_t0 (seismic.py:1253-1272)
+static int run_sweep(beatgpu_ctx* ctx, int B, const double* q)
+{
+    const beatgpu_layout& L = ctx->layout;
+    CK(cudaMemsetAsync(ctx->d_bad, 0, (size_t)B, ctx->stream));
+    SweepArgs s;
+    memset(&s, 0, sizeof(s));
+    s.n_dip = ctx->d_nd; s.n_strike = ctx->d_ns; s.patch_ofs = ctx->d_pofs; s.patch_size = ctx->d_psize;
+    s.n_subfaults = ctx->nsf; s.n_patches_total = ctx->np_total; s.max_np_sf = ctx->max_np_sf; s.B = B;
+    VarRef vel = var_ref(ctx, q, L.off_velocities, ctx->canon_vel);
+    VarRef nd = var_ref(ctx, q, L.off_nucleation_dip, ctx->canon_ndip);
+    VarRef nst = var_ref(ctx, q, L.off_nucleation_strike, ctx->canon_nstr);
+    VarRef tm = var_ref(ctx, q, L.off_time, ctx->canon_time);
+    s.vel = vel.p; s.vel_stride = vel.stride; s.is_slowness = 0;
+    s.nuc_dip = nd.p; s.nuc_dip_stride = nd.stride; s.nuc_strike = nst.p; s.nuc_strike_stride = nst.stride;
+    s.nuc_dip_idx = nullptr; s.nuc_strike_idx = nullptr; s.only_sf = -1;
+    s.time = tm.p; s.time_stride = tm.stride;
+    s.t0 = ctx->d_t0; s.n_iter = nullptr; s.violations = ctx->d_viol; s.chain_bad = ctx->d_bad;
+    return launch_sweep(ctx, s, B * ctx->nsf);
+}
+
+// per-chain inputs of the stacking kernels taken from q through the layout (fused-mode wiring)
+static void wire_chain_inputs(beatgpu_ctx* ctx, const WaveMap& w, const double* q, StackArgs& a)
+{
+    const beatgpu_layout& L = ctx->layout;
+    VarRef dur = var_ref(ctx, q, L.off_durations, ctx->canon_dur);
+    a.dur = dur.p; a.dur_sc = dur.stride;
+    for (int v = 0; v < L.n_slipvars; ++v) {
+        VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
+        a.slip[v] = sl.p; a.slip_sc[v] = sl.stride;
+    }
+    a.st = ctx->d_t0; a.st_sc = ctx->np_total; a.st_st = 0;
+    if (w.has_station) {
+        VarRef ts = var_ref(ctx, q, L.off_time_shifts, ctx->canon_ts);
+        a.corr = ts.p; a.corr_sc = ts.stride;
+    } else {
+        a.corr = nullptr; a.station_idx = nullptr;
+    }
+}
+
 // the fused path, everything on the device
 int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, double* logpts, double* like)
 {
@@ -919,22 +959,7 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
     VarRef hyp = var_ref(ctx, q, L.n_hypers ? L.off_hypers : -1, ctx->canon_hyp);
 
     if (!ctx->wmaps.empty()) {
-        CK(cudaMemsetAsync(ctx->d_bad, 0, (size_t)B, ctx->stream));
-        // ---- rupture onset times for all chains / subfaults (seismic.py:1253-1272)
-        SweepArgs s;
-        memset(&s, 0, sizeof(s));
-        s.n_dip = ctx->d_nd; s.n_strike = ctx->d_ns; s.patch_ofs = ctx->d_pofs; s.patch_size = ctx->d_psize;
-        s.n_subfaults = ctx->nsf; s.n_patches_total = ctx->np_total; s.max_np_sf = ctx->max_np_sf; s.B = B;
-        VarRef vel = var_ref(ctx, q, L.off_velocities, ctx->canon_vel);
-        VarRef nd = var_ref(ctx, q, L.off_nucleation_dip, ctx->canon_ndip);
-        VarRef nst = var_ref(ctx, q, L.off_nucleation_strike, ctx->canon_nstr);
-        VarRef tm = var_ref(ctx, q, L.off_time, ctx->canon_time);
-        s.vel = vel.p; s.vel_stride = vel.stride; s.is_slowness = 0;
-        s.nuc_dip = nd.p; s.nuc_dip_stride = nd.stride; s.nuc_strike = nst.p; s.nuc_strike_stride = nst.stride;
-        s.nuc_dip_idx = nullptr; s.nuc_strike_idx = nullptr; s.only_sf = -1;
-        s.time = tm.p; s.time_stride = tm.stride;
-        s.t0 = ctx->d_t0; s.n_iter = nullptr; s.violations = ctx->d_viol; s.chain_bad = ctx->d_bad;
-        if ((rc = launch_sweep(ctx, s, B * ctx->nsf))) return rc;
+        if ((rc = run_sweep(ctx, B, q))) return rc;
 
         // ---- per wavemap: gather + stack + residual + misfit (seismic.py:1275-1343)
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -943,19 +968,7 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
             memset(&a, 0, sizeof(a));
             fill_static(w, a, L.n_slipvars);
             a.B = B;
-            VarRef dur = var_ref(ctx, q, L.off_durations, ctx->canon_dur);
-            a.dur = dur.p; a.dur_sc = dur.stride;
-            for (int v = 0; v < L.n_slipvars; ++v) {
-                VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
-                a.slip[v] = sl.p; a.slip_sc[v] = sl.stride;
-            }
-            a.st = ctx->d_t0; a.st_sc = ctx->np_total; a.st_st = 0;
-            if (w.has_station) {
-                VarRef ts = var_ref(ctx, q, L.off_time_shifts, ctx->canon_ts);
-                a.corr = ts.p; a.corr_sc = ts.stride;
-            } else {
-                a.corr = nullptr; a.station_idx = nullptr;
-            }
+            wire_chain_inputs(ctx, w, q, a);
             a.hyp = hyp.p; a.hyp_sc = hyp.stride;
             a.logpts = logpts; a.logpts_sc = n_out; a.out_ofs = w.out_ofs;
             a.synth = nullptr; a.chain_bad = ctx->d_bad; a.violations = ctx->d_viol;
@@ -1026,6 +1039,32 @@ int beatgpu_ffi_loglike_batch(beatgpu_ctx* ctx, int B, const double* q, double* 
     CK(cudaMemcpyAsync(logpts, ctx->d_logpts, (size_t)B * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (like) CK(cudaMemcpyAsync(like, ctx->d_like, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return check_violations(ctx, "ffi_loglike_batch");
+}
+
+int beatgpu_ffi_synthetics_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* q, double* synthetics)
+{
+    GET_WMAP(wmap_id);
+    if (B <= 0 || !q || !synthetics) return fail(ctx, BEATGPU_E_ARG, "ffi_synthetics_batch: bad arguments");
+    if (!ctx->layout_set) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_synthetics_batch: set_fault / set_layout not called");
+    int rc;
+    if ((rc = check_lib(ctx, w, ctx->layout.n_slipvars))) return rc;
+    if (w.has_station && !ctx->layout.n_time_shifts) return fail(ctx, BEATGPU_E_ARG, "ffi_synthetics_batch: wavemap has station corrections but the layout has no time_shifts");
+    if ((rc = ensure_scratch(ctx, B))) return rc;
+    const size_t b_out = (size_t)B * w.nt * w.ns * sizeof(double);
+    if ((rc = ensure_tmp(ctx, 3, b_out))) return rc;
+    CK(cudaMemcpyAsync(ctx->d_q, q, (size_t)B * ctx->layout.n_params * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = run_sweep(ctx, B, ctx->d_q))) return rc;
+    StackArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_static(w, a, ctx->layout.n_slipvars);
+    a.B = B;
+    wire_chain_inputs(ctx, w, ctx->d_q, a);
+    a.synth = (double*)ctx->d_tmp[3];
+    a.chain_bad = ctx->d_bad; a.violations = ctx->d_viol;
+    if ((rc = launch_stack<true>(ctx, w, a))) return rc;
+    CK(cudaMemcpyAsync(synthetics, ctx->d_tmp[3], b_out, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return check_violations(ctx, "ffi_synthetics_batch");
 }
 
 int beatgpu_get_starttimes(beatgpu_ctx* ctx, int B, double* starttimes)

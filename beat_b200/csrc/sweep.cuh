@@ -64,13 +64,13 @@ __device__ inline int warp_fast_sweep(double* __restrict__ T, double* __restrict
                     const double cur = T[k];
                     const double f_h = fh[k];
                     const double diff = __dsub_rn(a, b);
-                    double cand;
-                    if (fabs(diff) >= f_h) {
-                        cand = __dadd_rn(lesser(a, b), f_h);
-                    } else {
-                        const double rad = __dsub_rn(c2[k], __dmul_rn(diff, diff));
-                        cand = __ddiv_rn(__dadd_rn(__dadd_rn(a, b), __dsqrt_rn(rad)), 2.0);
-                    }
+                    // both candidates evaluated branch-free (lanes of a diagonal diverge otherwise); the selection
+                    // keeps the reference's comparison `fabs(a-b) >= f*h` (false for NaN -> quadratic branch -> NaN).
+                    // x / 2.0 == x * 0.5 bit for bit in IEEE arithmetic.
+                    const double lin = __dadd_rn(lesser(a, b), f_h);
+                    const double rad = __dsub_rn(c2[k], __dmul_rn(diff, diff));
+                    const double quad = __dmul_rn(__dadd_rn(__dadd_rn(a, b), __dsqrt_rn(rad)), 0.5);
+                    const double cand = (fabs(diff) >= f_h) ? lin : quad;
                     T[k] = (cand < cur) ? cand : cur;
                 }
                 __syncwarp();

@@ -37,6 +37,7 @@ class BatchedFFILogLike:
         self.device = device
         self.prob_meta = None
         self.wmap_ids = []
+        self._wm_shapes = []
         self.n_params = 0
         self.npatches = 0
         self._torch_bufs = {}
@@ -73,6 +74,7 @@ class BatchedFFILogLike:
         for wm in prob["wavemaps"]:
             wid = ctx.add_wavemap(wm["nt"], wm["ns"], wm["interpolation"], wm.get("station_idx"), wm["hyper_idx"], wm["nsamples"])
             self.wmap_ids.append(wid)
+            self._wm_shapes.append((wm["nt"], wm["ns"]))
             if upload_libraries:
                 for iv, v in enumerate(self.slip_vars):
                     ctx.upload_gflib(wid, iv, np.ascontiguousarray(wm["G"][v]), code, wm["dur_min"], wm["dur_step"],
@@ -133,6 +135,17 @@ class BatchedFFILogLike:
             self._bound_stream = stream
         self.ctx.ffi_loglike_batch_dev(B, q_dev.data_ptr(), logpts_out.data_ptr(), like_out.data_ptr())
         return logpts_out, like_out
+
+    def get_synthetics(self, Q, wmap_index=0):
+        """Forward model only (reference: SeismicDistributerComposite.get_synthetics, outmode="array",
+        beat/models/seismic.py:1351-1507): Q [B, n_params] or [n_params] -> synthetics [B, nt, ns] / [nt, ns]."""
+        Q = np.ascontiguousarray(Q, dtype=np.float64)
+        single = Q.ndim == 1
+        if single:
+            Q = Q[None, :]
+        wm = self._wm_shapes[wmap_index]
+        out = self.ctx.ffi_synthetics_batch(self.wmap_ids[wmap_index], Q, wm[0], wm[1])
+        return out[0] if single else out
 
     def starttimes(self, B):
         return self.ctx.get_starttimes(B, self.npatches)

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "beatgpu_misfit_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "beatgpu_ffi_loglike_batch": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_ffi_loglike_batch_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "beatgpu_ffi_synthetics_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "beatgpu_get_starttimes": (C.c_int, [_P, C.c_int, _P]),
     "beatgpu_index_violations": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
@@ -300,6 +301,12 @@ class Context:
         """Device-pointer entry: enqueues on the ctx stream, no synchronisation."""
         self._check(self._lib.beatgpu_ffi_loglike_batch_dev(self._h, int(B), C.c_void_p(q_dev_ptr), C.c_void_p(logpts_dev_ptr),
                                                             C.c_void_p(like_dev_ptr or 0)))
+
+    def ffi_synthetics_batch(self, wmap, q, nt, ns):
+        q = _f64(q)
+        out = np.empty((q.shape[0], nt, ns))
+        self._check(self._lib.beatgpu_ffi_synthetics_batch(self._h, wmap, q.shape[0], _ptr(q), _ptr(out)))
+        return out
 
     def get_starttimes(self, B, npatches):
         out = np.empty((B, npatches))

@@ -192,6 +192,12 @@ int beatgpu_ffi_loglike_batch(beatgpu_ctx* ctx, int B, const double* q, double* 
 int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q_dev, double* logpts_dev,
                                   double* like_dev);
 
+/* Forward model only: replaces SeismicDistributerComposite.get_synthetics(point, outmode="array")
+ * (beat/models/seismic.py:1351-1507) for B chains of one wavemap: q [B, n_params] -> synthetics
+ * [B, nt, ns] (rupture sweep + stacking of all slip components, no residual / misfit).  Used between SMC
+ * stages to form the residuals the covariance update works on (seismic.py:1509-1534).              */
+int beatgpu_ffi_synthetics_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* q, double* synthetics);
+
 /* After a loglike batch: per-chain rupture start times [B, npatches] (Deterministic-style
  * inspection / parity of the sweep inside the fused path); host pointer.                     */
 int beatgpu_get_starttimes(beatgpu_ctx* ctx, int B, double* starttimes);

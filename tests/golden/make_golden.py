@@ -206,6 +206,28 @@ def gen_laplacian(out):
     out["lap_dims"] = np.array([nstr, ndip, hs, hd])
 
 
+def gen_noise_estimators(out):
+    """Per-stage covariance update operands (beat/covariance.py:716-771, beat/utility.py:1141-1161)."""
+    rng = np.random.default_rng(21)
+    n = 60
+    t = np.arange(n)
+    resid = np.sin(t / 5.0) * (0.5 + t / n) + 0.3 * rng.standard_normal(n)      # non-stationary residual
+    ws = n // 5                                                                   # covariance.py:316
+    out["nt_resid"] = resid
+    out["nt_window"] = np.int64(ws)
+    out["nt_rms_same"] = utility.running_window_rms(resid, window_size=ws, mode="same")
+    out["nt_autocov"] = bcov.autocovariance(resid / out["nt_rms_same"])
+    toe, stds = bcov.toeplitz_covariance(resid, ws)
+    out["nt_toeplitz"], out["nt_stds"] = toe, stds
+    C = bcov.non_toeplitz_covariance(resid, ws)
+    out["nt_cov"] = C
+    Cpsd = utility.ensure_cov_psd(C)
+    cov = heart.Covariance(data=Cpsd)
+    out["nt_cov_psd"] = Cpsd
+    out["nt_U"] = cov.chol_inverse
+    out["nt_logpdet"] = np.float64(cov.log_pdet)
+
+
 def main():
     out = {}
     gen_fast_sweep(out)
@@ -213,6 +235,7 @@ def main():
     gen_stack(out)
     gen_mvn(out)
     gen_laplacian(out)
+    gen_noise_estimators(out)
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "with", len(out), "arrays,", os.path.getsize(path), "bytes")

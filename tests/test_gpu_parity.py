@@ -381,3 +381,32 @@ def test_stack_execution_modes_vs_oracle(env, case, monkeypatch):
         got, _ = ev(Q)
         assert np.array_equal(got, logpts)
         ev.close()
+
+
+def test_get_synthetics_and_stage_weight_update():
+    """Stage boundary (seismic.py:1509-1534): synthetics at the MAP point -> residuals -> non-Toeplitz covariance ->
+    weights on the GPU -> uploaded -> next stage's llk equals the oracle evaluated with the host-computed weights."""
+    import torch
+    from beat_b200 import covariance as cv
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=5, subfaults=((4, 6, 2.0),), ns=60, ndur=4, seed=41, station_corrections=True)
+    Q = synthetic.draw_chains(prob, 12, seed=3)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    syn = ev.get_synthetics(Q)
+    for b in (0, 5, 11):
+        _, ref, _ = O.ffi_seismic_eval(prob, synthetic.split_point(prob, Q[b]), impl="port", return_synth=True)
+        np.testing.assert_allclose(syn[b], ref[0], rtol=1e-12, atol=1e-12 * np.abs(ref[0]).max())
+    np.testing.assert_array_equal(ev.get_synthetics(Q[5]), syn[5])
+    logpts, like = ev(Q)
+    imap = int(np.argmax(like))
+    wm = prob["wavemaps"][0]
+    resid = wm["data"] - syn[imap]
+    U_dev, lp_dev, _ = cv.weights_from_residuals_device(resid, device=torch.device("cuda", 0))
+    U_host, lp_host = cv.weights_from_residuals_host(resid)
+    np.testing.assert_allclose(lp_dev.cpu().numpy(), lp_host, rtol=1e-9)
+    np.testing.assert_allclose(U_dev.cpu().numpy(), U_host, rtol=1e-6, atol=1e-7 * np.abs(U_host).max())
+    ev.update_weights(0, U_dev.cpu().numpy(), lp_dev.cpu().numpy())
+    got, _ = ev(Q)
+    prob2 = dict(prob, wavemaps=[dict(wm, U=U_host, slog_pdet=lp_host)])
+    np.testing.assert_allclose(got, _oracle_logpts(prob2, Q), rtol=1e-7)
+    ev.close()

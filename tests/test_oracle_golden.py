@@ -136,3 +136,41 @@ def test_laplacian(golden):
     np.testing.assert_array_equal(L, golden["lap_L"])
     got = O.laplacian_logpt(L, float(golden["lap_sdet"]), golden["lap_u"], float(golden["lap_h"]))
     np.testing.assert_allclose(got, float(golden["lap_logpt"]), rtol=1e-14)
+
+
+def test_noise_estimators_host_mirrors(golden):
+    """Host mirrors of the per-stage covariance update (product side, set-up time) vs the reference's own output."""
+    from beat_b200 import covariance as cv
+    resid, ws = golden["nt_resid"], int(golden["nt_window"])
+    np.testing.assert_allclose(cv.running_window_rms(resid, ws, mode="same"), golden["nt_rms_same"], rtol=1e-14)
+    np.testing.assert_allclose(cv.autocovariance(resid / golden["nt_rms_same"]), golden["nt_autocov"], rtol=1e-11, atol=1e-14)
+    toe, stds = cv.toeplitz_covariance(resid, ws)
+    np.testing.assert_allclose(toe, golden["nt_toeplitz"], rtol=1e-11, atol=1e-14)
+    np.testing.assert_allclose(cv.non_toeplitz_covariance(resid, ws), golden["nt_cov"], rtol=1e-11, atol=1e-14)
+    U, lp = cv.weights_from_residuals_host(resid[None, :])
+    np.testing.assert_allclose(U[0], golden["nt_U"], rtol=1e-8, atol=1e-9 * np.abs(golden["nt_U"]).max())
+    np.testing.assert_allclose(lp[0], float(golden["nt_logpdet"]), rtol=1e-11)
+    # Covariance mirror: chol_inverse / log_pdet on the mvn golden matrices
+    for C, Ug, lg in zip(golden["mvn_C"], golden["mvn_U"], golden["mvn_logpdet"]):
+        c = cv.Covariance(data=C)
+        np.testing.assert_allclose(c.chol_inverse, Ug, rtol=1e-10, atol=1e-10 * np.abs(Ug).max())
+        np.testing.assert_allclose(c.log_pdet, lg, rtol=1e-13)
+    np.testing.assert_array_equal(cv.smoothing_operator_nearest_neighbor(5, 4, 2.0, 2.0), golden["lap_L"])
+    np.testing.assert_allclose(cv.log_determinant(golden["lap_L"].T * golden["lap_L"]), float(golden["lap_sdet"]), rtol=1e-13)
+
+
+def test_weights_from_residuals_torch_cpu(golden):
+    """The batched torch implementation (run here on CPU tensors) equals the host mirror."""
+    import torch
+    from beat_b200 import covariance as cv
+    rng = np.random.default_rng(3)
+    t = np.arange(60)
+    res = np.stack([golden["nt_resid"], np.cos(t / 3.0) * (1 + t / 40.0) + 0.2 * rng.standard_normal(60),
+                    rng.standard_normal(60) * np.linspace(0.5, 2.0, 60)])
+    U, lp, C = cv.weights_from_residuals_device(res, device=torch.device("cpu"))
+    Uh, lph = cv.weights_from_residuals_host(res)
+    np.testing.assert_allclose(C[0].numpy(), golden["nt_cov"], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(lp.numpy(), lph, rtol=1e-9)
+    for i in range(3):
+        # U is unique up to nothing (Cholesky with positive diagonal): compare directly and through U^T U = C^-1
+        np.testing.assert_allclose(U[i].numpy(), Uh[i], rtol=1e-6, atol=1e-7 * np.abs(Uh[i]).max())
