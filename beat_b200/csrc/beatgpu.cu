@@ -216,6 +216,8 @@ int launch_sweep(beatgpu_ctx* ctx, SweepArgs& a, int n_items)
 {
     size_t per_warp = (size_t)4 * a.max_np_sf * sizeof(double);
     int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (48 * 1024) / per_warp));
+    // latency-bound kernel: spread the warps over all SMs before stacking several on one
+    wpb = std::max(1, std::min(wpb, n_items / (2 * ctx->prop.multiProcessorCount)));
     size_t smem = per_warp * wpb;
     if (smem > 48 * 1024) {
         if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
