@@ -99,6 +99,17 @@ class Sweeper(_OpBase):
         return [(self.n_patch_dip * self.n_patch_strike,)]
 
 
+def _times2idxs(x, x_min, x_step, interpolation):
+    x = np.asarray(x, dtype=np.float64)
+    if interpolation == "nearest_neighbor":
+        return np.round((x - x_min) / x_step).astype("int16"), None
+    elif interpolation == "multilinear":
+        d = (x - x_min) / x_step
+        c = np.ceil(d).astype("int16")
+        return c, c - d
+    raise NotImplementedError("Interpolation scheme %s not implemented!" % interpolation)
+
+
 class SeismicGFLibrary(object):
     """Device-resident seismic GF library with the reference's stacking interface (beat/ffi/base.py:322-802).
 
@@ -126,6 +137,21 @@ class SeismicGFLibrary(object):
     ndurations = property(lambda self: self.dimensions[2])
     nstarttimes = property(lambda self: self.dimensions[3])
     nsamples = property(lambda self: self.dimensions[4])
+
+    # index helpers (host side, for inspection / library filling; the kernels do the same arithmetic per tap)
+    def starttimes2idxs(self, starttimes, interpolation="nearest_neighbor"):
+        """beat/ffi/base.py:486-521."""
+        return _times2idxs(starttimes, self.starttime_min, self.starttime_sampling, interpolation)
+
+    def durations2idxs(self, durations, interpolation="nearest_neighbor"):
+        """beat/ffi/base.py:535-568."""
+        return _times2idxs(durations, self.duration_min, self.duration_sampling, interpolation)
+
+    def idxs2durations(self, idxs):
+        return idxs * self.duration_sampling + self.duration_min          # base.py:523-527
+
+    def idxs2starttimes(self, idxs):
+        return idxs * self.starttime_sampling + self.starttime_min        # base.py:529-533
 
     def _context(self, interpolation):
         if interpolation not in _lib.INTERPOLATION:

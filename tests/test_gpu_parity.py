@@ -410,3 +410,36 @@ def test_get_synthetics_and_stage_weight_update():
     prob2 = dict(prob, wavemaps=[dict(wm, U=U_host, slog_pdet=lp_host)])
     np.testing.assert_allclose(got, _oracle_logpts(prob2, Q), rtol=1e-7)
     ev.close()
+
+
+def test_fault_geometry_helpers(golden):
+    """FaultGeometry index helpers (fault.py:610-632,722-752,866-894) + library index helpers vs golden / oracle."""
+    from beat_b200.fault import FaultGeometry, FaultOrdering, positions2idxs
+    from beat_b200.ops import SeismicGFLibrary
+    for cs in (1.0, 2.0, 2.5):
+        got = positions2idxs(golden["pos_in"], cs)
+        assert got.dtype == np.int16 and np.array_equal(got, golden[f"pos_idx_{cs}"])
+    fault = FaultGeometry(FaultOrdering(npls=[20, 15], npws=[10, 10], patch_sizes_strike=[2.0, 2.5], patch_sizes_dip=[2.0, 2.5]))
+    assert fault.npatches == 350 and fault.ordering.get_subfault_discretization(1) == (10, 15)
+    rng = np.random.default_rng(0)
+    B = 9
+    point = dict(velocities=rng.uniform(2.2, 4.5, (B, 350)), nucleation_dip=rng.uniform(0, 19.9, (B, 2)),
+                 nucleation_strike=np.stack([rng.uniform(0, 39.9, B), rng.uniform(0, 37.4, B)], axis=1), time=rng.uniform(-5, 5, (B, 2)))
+    for index, (nd, ns_, h) in enumerate(((10, 20, 2.0), (10, 15, 2.5))):
+        st = fault.point2starttimes(point, index=index)
+        assert st.shape == (B, nd, ns_)
+        for b in range(B):
+            di, si = O.fault_locations2idxs(point["nucleation_dip"][b, index], point["nucleation_strike"][b, index], h, h)
+            vel = point["velocities"][b, fault.cum_subfault_npatches[index]: fault.cum_subfault_npatches[index + 1]]
+            ref = O.fast_sweep(1.0 / vel, h, di, si, nd, ns_, impl="port").reshape(nd, ns_) + point["time"][b, index]
+            assert np.array_equal(st[b], ref)
+        one = fault.point2starttimes({k: v[3] for k, v in point.items()}, index=index)
+        assert np.array_equal(one, st[3])
+    st_min, st_step, dur_min, dur_step = golden["stack_axes"]
+    gfs = SeismicGFLibrary(golden["stack_rand_G"], dur_min, dur_step, st_min, st_step)
+    for tag, interp in (("nn", "nearest_neighbor"), ("ml", "multilinear")):
+        si, sf = gfs.starttimes2idxs(golden["stack_rand_starttimes"], interpolation=interp)
+        di, df = gfs.durations2idxs(golden["stack_rand_durations"], interpolation=interp)
+        assert np.array_equal(si, golden[f"stack_rand_{tag}_si"]) and np.array_equal(di, golden[f"stack_rand_{tag}_di"])
+        if sf is not None:
+            assert np.array_equal(sf, golden[f"stack_rand_{tag}_sf"]) and np.array_equal(df, golden[f"stack_rand_{tag}_df"])
