@@ -154,13 +154,15 @@ class BatchedMetropolis:
 
 
 def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_variation=1.0, tune_interval=None, seed=0,
-               sample_factor_final_stage=1, max_stages=200, initial_population=None, update_weights=None, log=None):
+               sample_factor_final_stage=1, max_stages=200, initial_population=None, update_weights=None, log=None,
+               on_step=None):
     """Batched restatement of ``smc_sample``'s stage loop (beat/sampler/smc.py:459-546).
 
     Returns dict(population [n_chains, n_params], likelihoods [n_chains], logpts, betas, n_evals, acceptance).
     ``update_weights(map_point) -> None`` mirrors the ``update`` hook (smc.py:492-503): called with the MAP end
     point after each stage; the caller re-uploads weights (``BatchedFFILogLike.update_weights``) and the end points
-    are re-evaluated."""
+    are re-evaluated.  ``on_step(stage, step, q, logpts, like)`` is called after every lock-step Metropolis step with
+    this rank's device tensors -- the hook for a trace backend (``beat_b200.backend.BatchedNumpyChains``)."""
     import torch
     from . import distributed as D
     device = device if device is not None else torch.device("cpu")
@@ -213,9 +215,11 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         mh.steps_until_tune = mh.tune_interval
         mh.accepted.zero_()
         n_acc = 0.0
-        for _ in range(draws):
+        for istep in range(draws):
             q, logpts, like, acc = mh.step(q, logpts, like)
             n_acc += float(acc.double().mean())
+            if on_step is not None:
+                on_step(stage + 1, istep, q, logpts, like)
         acc_hist.append(n_acc / max(1, draws))
         beta = new_beta
         betas.append(beta)
