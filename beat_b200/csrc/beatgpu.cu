@@ -458,12 +458,15 @@ int beatgpu_sync(beatgpu_ctx* ctx)
     return BEATGPU_OK;
 }
 
-int beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream)
+int beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream, int external)
 {
     if (!ctx) return BEATGPU_E_ARG;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (cuda_stream) {
+    if (external) {
+        // use the caller's stream handle as is; 0 is the (legacy) default stream, which is what torch's
+        // current stream is unless the caller entered a torch.cuda.stream() context
         ctx->stream = (cudaStream_t)cuda_stream;
         ctx->own_stream = false;
     } else {

@@ -130,8 +130,8 @@ class BatchedFFILogLike:
         if like_out is None:
             like_out = torch.empty((B,), dtype=torch.float64, device=q_dev.device)
         stream = torch.cuda.current_stream(q_dev.device).cuda_stream
-        if getattr(self, "_bound_stream", None) != stream:
-            self.ctx.set_stream(stream)
+        if getattr(self, "_bound_stream", -1) != stream:
+            self.ctx.set_stream(stream, external=True)      # order our kernels with torch's work on its current stream
             self._bound_stream = stream
         self.ctx.ffi_loglike_batch_dev(B, q_dev.data_ptr(), logpts_out.data_ptr(), like_out.data_ptr())
         return logpts_out, like_out

@@ -64,7 +64,7 @@ _SIGNATURES = {
     "beatgpu_ctx_destroy": (None, [_P]),
     "beatgpu_last_error": (C.c_char_p, [_P]),
     "beatgpu_sync": (C.c_int, [_P]),
-    "beatgpu_set_stream": (C.c_int, [_P, _P]),
+    "beatgpu_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "beatgpu_device_info": (C.c_int, [_P, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "beatgpu_set_fault": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_set_layout": (C.c_int, [_P, C.POINTER(Layout), _P]),
@@ -166,8 +166,9 @@ class Context:
     def sync(self):
         self._check(self._lib.beatgpu_sync(self._h))
 
-    def set_stream(self, cuda_stream_ptr):
-        self._check(self._lib.beatgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0)))
+    def set_stream(self, cuda_stream_ptr, external=True):
+        """external=True: enqueue on the given CUDA stream handle (0 = default stream); False: private stream."""
+        self._check(self._lib.beatgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0), 1 if external else 0))
 
     def device_info(self):
         n = C.c_int()

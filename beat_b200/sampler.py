@@ -111,8 +111,12 @@ class BatchedMetropolis:
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed))
         self.beta = 1.0
-        self.n_evals = 0
+        self._n_evals = torch.zeros((), dtype=torch.float64, device=self.device)   # device-side counter: no host sync per step
         self.chol = None
+
+    @property
+    def n_evals(self):
+        return int(self._n_evals.item())
 
     def set_proposal_covariance(self, cov):
         """MultivariateNormal proposal (sampler/base.py:163-167): draws = z @ chol(cov).T."""
@@ -122,7 +126,7 @@ class BatchedMetropolis:
     def initial_llk(self, q):
         """Stage 0: evaluate the start population; non-finite llk raises (metropolis.py:277-284)."""
         logpts, like = self.evaluator(q)
-        self.n_evals += q.shape[0]
+        self._n_evals += q.shape[0]
         if not bool(self.torch.isfinite(like).all()):
             raise ValueError("Got NaN in likelihood evaluation! Invalid model definition? Or starting point outside prior bounds!")
         return logpts, like
@@ -141,7 +145,7 @@ class BatchedMetropolis:
         # out-of-prior proposals are rejected without being trusted: evaluate a safe copy (the previous point) there
         q_eval = torch.where(inside[:, None], q, q0).contiguous()
         logpts, like = self.evaluator(q_eval)
-        self.n_evals += int(inside.sum())
+        self._n_evals += inside.sum()
         log_u = torch.log(torch.rand(self.n_chains, dtype=torch.float64, device=self.device, generator=self.gen))
         ratio = self.beta * (like - like0)
         accept = inside & torch.isfinite(ratio) & (log_u < ratio)          # pymc metrop_select
@@ -214,13 +218,13 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         draws = n_steps * (sample_factor_final_stage if final else 1)
         mh.steps_until_tune = mh.tune_interval
         mh.accepted.zero_()
-        n_acc = 0.0
+        n_acc = torch.zeros((), dtype=torch.float64, device=device)
         for istep in range(draws):
             q, logpts, like, acc = mh.step(q, logpts, like)
-            n_acc += float(acc.double().mean())
+            n_acc += acc.double().mean()                      # stays on the device; read once per stage
             if on_step is not None:
                 on_step(stage + 1, istep, q, logpts, like)
-        acc_hist.append(n_acc / max(1, draws))
+        acc_hist.append(float(n_acc.item()) / max(1, draws))
         beta = new_beta
         betas.append(beta)
         stage += 1

@@ -391,6 +391,29 @@ def run_gpu_arm(args):
     host_like = like_pin.numpy().copy()
     assert np.isfinite(host_like).all()
 
+    # ---------------- the same evaluation inside the lock-step Metropolis driver (propose -> bounds -> eval -> accept),
+    # everything resident on the device: what a sampler stage actually achieves per GPU
+    from beat_b200.sampler import BatchedMetropolis
+    lower = np.concatenate([prob["priors"][n][0] for n, _ in prob["var_order"]])
+    upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
+    mh = BatchedMetropolis(ev.eval_device, lower, upper, B, device=device, tune=True, tune_interval=5, seed=rank)
+    mh.chol = torch.diag(torch.as_tensor((upper - lower) * 0.005, device=device))
+    mh.beta = 0.1
+    qs = q_dev[0].clone()
+    lps, lks = mh.initial_llk(qs)
+    for _ in range(args.warmup):
+        qs, lps, lks, _ = mh.step(qs, lps, lks)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        qs, lps, lks, _ = mh.step(qs, lps, lks)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if n_gpus > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sampler_value = n_gpus * B * args.steps / (float(t.item()) / 1e3)
+
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -418,6 +441,8 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * prob["n_params"] * 8,
                     "d2h_bytes_per_step": B * (n_out + 1) * 8},
             "gpu_launches": int(launches),
+            "sampler_step": {"value": sampler_value, "unit": "chain-steps/s",
+                             "what": "lock-step Metropolis step (proposal + bounds + batched eval + accept) with the population resident on the device"},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "gf_stack_chunk_kernel+misfit_kernel (GF gather/stack + misfit)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -59,8 +59,10 @@ int         beatgpu_ctx_create(int device, beatgpu_ctx** out);
 void        beatgpu_ctx_destroy(beatgpu_ctx* ctx);
 const char* beatgpu_last_error(const beatgpu_ctx* ctx);    /* ctx may be NULL: last create() error */
 int         beatgpu_sync(beatgpu_ctx* ctx);                 /* cudaStreamSynchronize on the ctx stream */
-/* make the ctx enqueue on an existing CUDA stream (e.g. torch's current stream); 0 = own stream */
-int         beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream);
+/* external != 0: enqueue on the caller's CUDA stream `cuda_stream` (e.g. torch's current stream; the handle 0 is
+ * the default stream) so the library's kernels are ordered with the caller's work on that stream;
+ * external == 0: go back to a private non-blocking stream (cuda_stream ignored).                       */
+int         beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream, int external);
 /* number of SMs, device name; for sizing/reporting */
 int         beatgpu_device_info(beatgpu_ctx* ctx, int* n_sm, char* name, int name_len);
 

@@ -443,3 +443,32 @@ def test_fault_geometry_helpers(golden):
         assert np.array_equal(si, golden[f"stack_rand_{tag}_si"]) and np.array_equal(di, golden[f"stack_rand_{tag}_di"])
         if sf is not None:
             assert np.array_equal(sf, golden[f"stack_rand_{tag}_sf"]) and np.array_equal(df, golden[f"stack_rand_{tag}_df"])
+
+
+def test_eval_device_is_stream_ordered_with_torch():
+    """eval_device must run on torch's current stream (the default stream has handle 0): inputs produced by queued
+    torch work are seen, and torch work queued afterwards sees the outputs -- without any host synchronisation."""
+    import torch
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=4, subfaults=((4, 6, 2.0),), ns=32, ndur=4, seed=55)
+    Q = synthetic.draw_chains(prob, 64, seed=9)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    ref_lp, ref_like = ev(Q)
+    dev = torch.device("cuda", 0)
+    q_host = torch.from_numpy(Q).pin_memory()
+    for use_side_stream in (False, True):
+        stream = torch.cuda.Stream(dev) if use_side_stream else torch.cuda.current_stream(dev)
+        with torch.cuda.stream(stream):
+            q_dev = torch.zeros(Q.shape, dtype=torch.float64, device=dev)
+            a = torch.randn(4096, 4096, device=dev)
+            for _ in range(30):                       # keep the stream busy so the copy below is still pending
+                a = (a @ a).clamp_(-1, 1)
+            q_dev.copy_(q_host, non_blocking=True)
+            lp, like = ev.eval_device(q_dev)
+            total = like.sum()                        # torch work queued behind our kernels
+            got_like, got_total = like.cpu().numpy(), float(total.cpu())
+            got_lp = lp.cpu().numpy()
+        assert np.array_equal(got_lp, ref_lp), use_side_stream
+        assert np.array_equal(got_like, ref_like)
+        np.testing.assert_allclose(got_total, ref_like.sum(), rtol=1e-12)
+    ev.close()
