@@ -51,7 +51,7 @@ def usable_cores():
         n = min(n, max(1, int(psutil.virtual_memory().available / 2**30 / 1.5)))
     except Exception:
         pass
-    return max(1, min(n, int(os.environ.get("BENCH_MAX_CORES", "64"))))
+    return max(1, min(n, int(os.environ.get("BENCH_MAX_CORES", "256"))))
 
 
 def _worker_init():
@@ -109,7 +109,8 @@ def workload_config(args, n_gpus, chains):
                     "starttimes, uparr+uperp, %s, exponential covariance%s" % (CONFIG.upper(), npatch, nd, nstr, h, a["nt"], a["ns"],
                                                                             a["ndur"], a["nst"], args.interpolation, extra),
         "chains_per_gpu": chains, "global_chains": chains * n_gpus, "parallelism": "chains sharded x%d" % n_gpus,
-        "gf_storage": args.store, "accumulate": "f64", "interpolation": args.interpolation,
+        "gf_storage": args.store, "interpolation": args.interpolation,
+        "accumulate": ("f32 FMA per patch pair, f64 running sum" if args.store == "f32" else "f64 FMA") + "; sweep, residual, misfit in f64",
         "l2": "inputs>L2 (GF library %.1f GB per GPU; q rotates between steps)" % (lib_bytes(a, args.store) / 1e9),
     }
 
@@ -361,12 +362,12 @@ def run_gpu_arm(args):
     barrier()
     t_wall1 = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
+    launches = ev.ctx.launch_count() - launches0
     # duration of the dominant kernel (event pair recorded inside the library around the stack + misfit launches,
     # on the same stream): read for a few more steps OUTSIDE the timed region so the event sync costs nothing there
     for i in range(min(5, args.steps)):
         step_resident(i)
         stack_ms.append(ev.ctx.last_stack_ms())
-    launches = ev.ctx.launch_count() - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=device)
     if n_gpus > 1:
