@@ -15,6 +15,7 @@
 #include "sweep.cuh"
 #include "stack.cuh"
 #include "aux.cuh"
+#include "gemm.cuh"
 
 using namespace beatgpu;
 
@@ -52,7 +53,8 @@ struct Geodetic {
     double *d_data = nullptr, *d_odw = nullptr, *d_UT = nullptr, *d_slog = nullptr;
     long* d_UT_ofs = nullptr;
     int *d_lo = nullptr, *d_hi = nullptr, *d_upper = nullptr, *d_nsamp = nullptr, *d_hyper_idx = nullptr;
-    std::vector<int> lo, hi;
+    std::vector<int> lo, hi, h_upper, h_nsamp, h_hyper_idx;
+    std::vector<double> h_slog;
     std::vector<long> ut_ofs;
     long ut_total = 0;
     int out_ofs = 0;
@@ -107,6 +109,7 @@ struct beatgpu_ctx {
     bool persistent = false;        // BEATGPU_PERSISTENT=1: fused kernel with one resident CTA wave walking the items
     int stack_mode = 1;             // 0 = fused kernel (CTA per target x chain), 1 = patch-chunked warps + misfit pass
     int chunk_patches = 32;         // BEATGPU_CHUNK: target patches per chunk (<= 32)
+    int geo_mode = 1;               // 1 = FP64 tensor-core GEMM tiles (BEATGPU_GEO_MODE=mma), 0 = one CTA per (chain, dataset)
     double* d_partial = nullptr;    // [B, nt, nchunk, ns] scratch of the chunked path
     size_t partial_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -419,6 +422,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     memset(&c->layout, 0, sizeof(c->layout));
     if (const char* e = getenv("BEATGPU_PERSISTENT")) c->persistent = atoi(e) != 0;
     if (const char* e = getenv("BEATGPU_STACK_MODE")) c->stack_mode = (strcmp(e, "fused") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
+    if (const char* e = getenv("BEATGPU_GEO_MODE")) c->geo_mode = (strcmp(e, "simple") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) c->chunk_patches = v; }
     (void)ctx;
     *out = c;
@@ -737,6 +741,10 @@ int beatgpu_set_geodetic(beatgpu_ctx* ctx, int nobs, int nds, const int32_t* slo
     if ((rc = upload_vec(ctx, &g.d_UT_ofs, g.ut_ofs.data(), nds))) return rc;
     if ((rc = upload_vec(ctx, &g.d_nsamp, nsamples, nds))) return rc;
     if ((rc = upload_vec(ctx, &g.d_hyper_idx, hyper_idx, nds))) return rc;
+    g.h_nsamp.assign(nsamples, nsamples + nds);
+    g.h_hyper_idx.assign(hyper_idx, hyper_idx + nds);
+    for (int d = 0; d < nds; ++d)
+        if (hyper_idx[d] < 0 || hyper_idx[d] >= ctx->layout.n_hypers) return fail(ctx, BEATGPU_E_ARG, "set_geodetic: hyper_idx[%d] out of range", d);
     g.set = true;
     assign_out_offsets(ctx);
     return beatgpu_update_geodetic_weights(ctx, U_concat, slog_pdet);
@@ -766,6 +774,8 @@ int beatgpu_update_geodetic_weights(beatgpu_ctx* ctx, const double* U_concat, co
     if ((rc = upload_vec(ctx, &g.d_UT, UT.data(), UT.size()))) return rc;
     if ((rc = upload_vec(ctx, &g.d_upper, upper.data(), g.nds))) return rc;
     if ((rc = upload_vec(ctx, &g.d_slog, slog_pdet, g.nds))) return rc;
+    g.h_upper = upper;
+    g.h_slog.assign(slog_pdet, slog_pdet + g.nds);
     return BEATGPU_OK;
 }
 
@@ -987,7 +997,48 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
         ctx->ev_valid = true;
     }
 
-    if (ctx->geo.set) {
+    if (ctx->geo.set && ctx->geo_mode == 1) {
+        // batched over chains the geodetic composite is two GEMMs: FP64 tensor-core tiles (gemm.cuh)
+        Geodetic& g = ctx->geo;
+        const int mt_max = (g.max_n + kGemmTile - 1) / kGemmTile;
+        if ((rc = ensure_tmp(ctx, 4, (size_t)B * g.nobs * sizeof(double)))) return rc;          // R [B, nobs]
+        if ((rc = ensure_tmp(ctx, 5, (size_t)B * mt_max * sizeof(double)))) return rc;          // partial norms
+        GemmArgs ga;
+        memset(&ga, 0, sizeof(ga));
+        ga.M = g.nobs; ga.N = B; ga.K = ctx->np_total; ga.n_parts = L.n_slipvars;
+        ga.a_sm = 1; ga.a_sk = g.nobs; ga.b_sk = 1;
+        for (int v = 0; v < L.n_slipvars; ++v) {
+            ga.A[v] = g.G[v];                                   // G_v [np, nobs]: A(m=obs, k=patch) = G_v[k*nobs + m]
+            VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
+            ga.B[v] = sl.p; ga.b_sn[v] = sl.stride;             // slip_v(k=patch, n=chain) = q[n*stride + off + k]
+        }
+        ga.upper = 0; ga.data = g.d_data; ga.odw = g.d_odw; ga.R = (double*)ctx->d_tmp[4]; ga.ldr = g.nobs;
+        dim3 grid1((B + kGemmTile - 1) / kGemmTile, (g.nobs + kGemmTile - 1) / kGemmTile);
+        dgemm_tile_kernel<0><<<grid1, kGemmThreads, 0, ctx->stream>>>(ga);
+        CKL();
+        for (int d = 0; d < g.nds; ++d) {
+            const int n = g.hi[d] - g.lo[d];
+            const int mt = (n + kGemmTile - 1) / kGemmTile;
+            GemmArgs gb;
+            memset(&gb, 0, sizeof(gb));
+            gb.M = n; gb.N = B; gb.K = n; gb.n_parts = 1;
+            gb.A[0] = g.d_UT + g.ut_ofs[d]; gb.a_sm = 1; gb.a_sk = n;          // U(m, k) = UT[k*n + m]
+            gb.B[0] = (const double*)ctx->d_tmp[4] + g.lo[d]; gb.b_sk = 1; gb.b_sn[0] = g.nobs;
+            gb.upper = g.h_upper[d];
+            gb.qpart = (double*)ctx->d_tmp[5]; gb.n_mtiles = mt;
+            dim3 grid2((B + kGemmTile - 1) / kGemmTile, mt);
+            dgemm_tile_kernel<1><<<grid2, kGemmThreads, 0, ctx->stream>>>(gb);
+            CKL();
+            GeoFinishArgs f;
+            memset(&f, 0, sizeof(f));
+            f.B = B; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];
+            f.slog_pdet = g.h_slog[d]; f.nsamp = g.h_nsamp[d]; f.hyper_idx = g.h_hyper_idx[d];
+            f.hyp = hyp.p; f.hyp_sc = hyp.stride;
+            f.logpts = logpts; f.logpts_sc = n_out; f.out_col = g.out_ofs + d;
+            geodetic_finish_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(f);
+            CKL();
+        }
+    } else if (ctx->geo.set) {
         Geodetic& g = ctx->geo;
         GeoArgs a;
         memset(&a, 0, sizeof(a));

@@ -79,7 +79,12 @@ METRIC = "forward+loglike evals/sec (FFI seismic 200-patch)"
 UNIT = "evals/s"
 
 
+NOISE = "exponential"
+
+
 def metric_name():
+    if NOISE != "exponential":
+        return "forward+loglike evals/sec (%s, %s covariance; not the BASELINE metric)" % (CONFIG.upper(), NOISE)
     return METRIC if CONFIG == "c3" else "forward+loglike evals/sec (%s, not the BASELINE metric)" % CONFIG.upper()
 
 
@@ -302,7 +307,7 @@ def run_gpu_arm(args):
 
     a = c3_args(args.quick)
     B = args.chains
-    prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, build_library=False, **a)
+    prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, build_library=False, noise=args.noise, **a)
     ev = BatchedFFILogLike.from_problem(prob, device=local_rank, store_dtype="float32" if args.store == "f32" else "float64",
                                         upload_libraries=False)
     log("filling %.1f GB of synthetic GF library in HBM" % (lib_bytes(a, args.store) / 1e9))
@@ -429,7 +434,7 @@ def run_gpu_arm(args):
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
-                if (CONFIG == "c3" and not args.quick and tj.get("chains") == B and tj.get("store") == args.store
+                if (CONFIG == "c3" and NOISE == "exponential" and not args.quick and tj.get("chains") == B and tj.get("store") == args.store
                         and tj.get("interpolation") == args.interpolation):
                     traffic, tnote, l2_bytes = tj.get("dram_bytes_per_launch"), tj.get("note"), tj.get("l2_to_sm_bytes")
             except Exception:
@@ -478,10 +483,12 @@ def main():
     ap.add_argument("--interpolation", default="multilinear", choices=["multilinear", "nearest_neighbor"])
     ap.add_argument("--quick", action="store_true", help="tiny shapes (development only; not a valid benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--noise", default="exponential", choices=["exponential", "variance", "dense"],
+                    help="data covariance structure (exponential = BASELINE config; dense = full non-Toeplitz, for the record)")
     ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"], help="c3 = BASELINE.json metric; c4/c5 for the record")
     args = ap.parse_args()
-    global CONFIG
-    CONFIG = args.config
+    global CONFIG, NOISE
+    CONFIG, NOISE = args.config, args.noise
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference_arm(args)

@@ -220,21 +220,24 @@ def test_fused_loglike_vs_oracle(case, store, rtol):
     ev.close()
 
 
-def test_fused_joint_geodetic_laplacian():
-    """Config-4 shape: seismic + geodetic static (dense non-Toeplitz C) + laplacian prior, all in one call."""
+@pytest.mark.parametrize("geo_mode", ["mma", "simple"])
+@pytest.mark.parametrize("nobs,B", [([60, 45], 16), ([150, 70, 5], 70), ([64], 129)])
+def test_fused_joint_geodetic_laplacian(geo_mode, nobs, B, monkeypatch):
+    """Config-4 shape: seismic + geodetic static (dense non-Toeplitz C) + laplacian prior, all in one call.
+    geo_mode "mma" = FP64 tensor-core GEMM tiles over all chains, "simple" = one CTA per (chain, dataset)."""
     from beat_b200.engine import BatchedFFILogLike
-    prob = synthetic.make_problem(nt=4, subfaults=((5, 7, 2.0),), ns=24, ndur=4, geodetic=dict(nobs=[60, 45]), laplacian=True, seed=3)
-    B = 16
+    monkeypatch.setenv("BEATGPU_GEO_MODE", geo_mode)
+    prob = synthetic.make_problem(nt=4, subfaults=((5, 7, 2.0),), ns=24, ndur=4, geodetic=dict(nobs=nobs), laplacian=True, seed=3)
     Q = synthetic.draw_chains(prob, B, seed=6)
     ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
     logpts, like = ev(Q)
-    assert logpts.shape == (B, 4 + 2 + 1)
+    assert logpts.shape == (B, 4 + len(nobs) + 1)
     for b in range(B):
         pt = synthetic.split_point(prob, Q[b])
         ref = np.concatenate([O.ffi_seismic_eval(prob, pt, impl="port"), O.ffi_geodetic_eval(prob["geodetic"], pt),
                               [O.ffi_laplacian_eval(prob["laplacian"], pt, prob["slip_vars"])]])
         np.testing.assert_allclose(logpts[b], ref, rtol=1e-10)
-        np.testing.assert_allclose(like[b], ref.sum(), rtol=1e-10)
+        np.testing.assert_allclose(like[b], ref.sum(), rtol=1e-10, atol=1e-10 * np.abs(ref).sum())
     ev.close()
 
 
