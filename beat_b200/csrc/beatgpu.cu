@@ -307,11 +307,44 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
     }
     ca.partial = ctx->d_partial;
     int rc;
+    const bool dense_gemm = a.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && a.B >= 32;
+    if (dense_gemm) {       // scratch first: ensure_tmp may free + allocate (implicitly synchronising)
+        const int mt = (a.ns + kGemmTile - 1) / kGemmTile;
+        if ((rc = ensure_tmp(ctx, 4, (size_t)a.nt * a.B * a.ns * sizeof(double)))) return rc;
+        if ((rc = ensure_tmp(ctx, 5, (size_t)a.nt * a.B * mt * sizeof(double)))) return rc;
+    }
     if (w.store_dtype == BEATGPU_F32)
         rc = (w.interp == BEATGPU_NEAREST) ? launch_chunk_nvar<float, 1>(ctx, ca) : launch_chunk_nvar<float, 4>(ctx, ca);
     else
         rc = (w.interp == BEATGPU_NEAREST) ? launch_chunk_nvar<double, 1>(ctx, ca) : launch_chunk_nvar<double, 4>(ctx, ca);
     if (rc) return rc;
+    if (dense_gemm) {
+        // full (non-Toeplitz) covariance: |U_t r|^2 for all chains is a GEMM per target -> FP64 tensor cores
+        const int mt = (a.ns + kGemmTile - 1) / kGemmTile;
+        double* R = (double*)ctx->d_tmp[4];
+        double* qpart = (double*)ctx->d_tmp[5];
+        residual_from_partials_kernel<<<(unsigned)((long)a.nt * a.B), 128, 0, ctx->stream>>>(ctx->d_partial, a.data, R, a.B, a.nt, a.ns, ca.nchunk);
+        CKL();
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.M = a.ns; g.N = a.B; g.K = a.ns; g.n_parts = 1;
+        g.A[0] = a.W; g.a_sm = 1; g.a_sk = a.ns; g.a_batch = (long)a.ns * a.ns;        // U_t(m, k) = W[t][k*ns + m]
+        g.B[0] = R; g.b_sk = 1; g.b_sn[0] = a.ns; g.b_batch = (long)a.B * a.ns;          // R_t(k, c) = R[t][c][k]
+        g.upper = a.dense_upper;
+        g.qpart = qpart; g.n_mtiles = mt; g.q_batch = (long)a.B * mt;
+        dim3 grid((a.B + kGemmTile - 1) / kGemmTile, mt, a.nt);
+        dgemm_tile_kernel<1><<<grid, kGemmThreads, 0, ctx->stream>>>(g);
+        CKL();
+        SeisFinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.B = a.B; f.nt = a.nt; f.n_mtiles = mt; f.qpart = qpart;
+        f.slog_pdet = a.slog_pdet; f.nsamp = a.nsamp; f.hyper_idx = a.hyper_idx;
+        f.hyp = a.hyp; f.hyp_sc = a.hyp_sc; f.chain_bad = a.chain_bad;
+        f.logpts = a.logpts; f.logpts_sc = a.logpts_sc; f.out_ofs = a.out_ofs;
+        seismic_finish_kernel<<<(unsigned)(((long)a.B * a.nt + 127) / 128), 128, 0, ctx->stream>>>(f);
+        CKL();
+        return BEATGPU_OK;
+    }
     MisfitArgs m;
     memset(&m, 0, sizeof(m));
     m.B = a.B; m.nt = a.nt; m.ns = a.ns;
@@ -896,18 +929,42 @@ int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* res
     if ((rc = ensure_tmp(ctx, 0, b_r)) || (rc = ensure_tmp(ctx, 1, b_h)) || (rc = ensure_tmp(ctx, 2, b_o))) return rc;
     CK(cudaMemcpyAsync(ctx->d_tmp[0], residuals, b_r, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tmp[1], hypers, b_h, cudaMemcpyHostToDevice, ctx->stream));
-    MisfitArgs a;
-    memset(&a, 0, sizeof(a));
-    a.B = B; a.nt = w.nt; a.ns = w.ns;
-    a.resid = (const double*)ctx->d_tmp[0];
-    a.hyp = (const double*)ctx->d_tmp[1]; a.hyp_sc = n_hypers; a.hyper_idx = w.d_hyper_idx;
-    a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
-    a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
-    a.logpts = (double*)ctx->d_tmp[2]; a.logpts_sc = w.nt; a.out_ofs = 0;
-    const size_t smem = (size_t)w.ns * sizeof(double);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
-    CKL();
+    if (w.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && B >= 32) {
+        // dense weights: Z_t = U_t R_t for all chains on the FP64 tensor cores, straight from the caller's layout
+        const int mt = (w.ns + kGemmTile - 1) / kGemmTile;
+        if ((rc = ensure_tmp(ctx, 5, (size_t)w.nt * B * mt * sizeof(double)))) return rc;
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.M = w.ns; g.N = B; g.K = w.ns; g.n_parts = 1;
+        g.A[0] = w.d_W; g.a_sm = 1; g.a_sk = w.ns; g.a_batch = (long)w.ns * w.ns;
+        g.B[0] = (const double*)ctx->d_tmp[0]; g.b_sk = 1; g.b_sn[0] = (long)w.nt * w.ns; g.b_batch = w.ns;   // resid[c][t][k]
+        g.upper = w.dense_upper;
+        g.qpart = (double*)ctx->d_tmp[5]; g.n_mtiles = mt; g.q_batch = (long)B * mt;
+        dim3 grid((B + kGemmTile - 1) / kGemmTile, mt, w.nt);
+        dgemm_tile_kernel<1><<<grid, kGemmThreads, 0, ctx->stream>>>(g);
+        CKL();
+        SeisFinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.B = B; f.nt = w.nt; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];
+        f.slog_pdet = w.d_slog_pdet; f.nsamp = w.d_nsamp; f.hyper_idx = w.d_hyper_idx;
+        f.hyp = (const double*)ctx->d_tmp[1]; f.hyp_sc = n_hypers; f.chain_bad = nullptr;
+        f.logpts = (double*)ctx->d_tmp[2]; f.logpts_sc = w.nt; f.out_ofs = 0;
+        seismic_finish_kernel<<<(unsigned)(((long)B * w.nt + 127) / 128), 128, 0, ctx->stream>>>(f);
+        CKL();
+    } else {
+        MisfitArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = B; a.nt = w.nt; a.ns = w.ns;
+        a.resid = (const double*)ctx->d_tmp[0];
+        a.hyp = (const double*)ctx->d_tmp[1]; a.hyp_sc = n_hypers; a.hyper_idx = w.d_hyper_idx;
+        a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
+        a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
+        a.logpts = (double*)ctx->d_tmp[2]; a.logpts_sc = w.nt; a.out_ofs = 0;
+        const size_t smem = (size_t)w.ns * sizeof(double);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
+        CKL();
+    }
     CK(cudaMemcpyAsync(logpts, ctx->d_tmp[2], b_o, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return BEATGPU_OK;

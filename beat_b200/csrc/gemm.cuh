@@ -12,6 +12,7 @@
 // through shared memory.  Upper-triangular U skips the K tiles left of the diagonal.
 #pragma once
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 namespace beatgpu {
@@ -36,6 +37,8 @@ struct GemmArgs {
     const double* data; const double* odw; double* R; long ldr;
     // epilogue 1: partial column norms  qpart[(n*n_mtiles + mtile)] = sum over the tile's rows of acc^2
     double* qpart; int n_mtiles;
+    // batching over blockIdx.z (e.g. the targets of a wavemap): element strides of A[0], B[0], qpart per batch index
+    long a_batch, b_batch, q_batch;
 };
 
 template <int EPI>
@@ -56,8 +59,8 @@ __global__ void __launch_bounds__(kGemmThreads) dgemm_tile_kernel(GemmArgs g)
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int part = 0; part < g.n_parts; ++part) {
-        const double* Ap = g.A[part];
-        const double* Bp = g.B[part];
+        const double* Ap = g.A[part] + (long)blockIdx.z * g.a_batch;
+        const double* Bp = g.B[part] + (long)blockIdx.z * g.b_batch;
         const long bsn = g.b_sn[part];
         for (int k0 = 0; k0 < g.K; k0 += kGemmK) {
             if (g.upper && k0 + kGemmK <= m0) continue;            // whole tile strictly left of the diagonal: zeros
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(kGemmThreads) dgemm_tile_kernel(GemmArgs g)
         __syncthreads();
         if (tid < kGemmTile) {
             const int n = n0 + tid;
-            if (n < g.N) g.qpart[(long)n * g.n_mtiles + blockIdx.y] = (colsum[0][tid] + colsum[1][tid]) + (colsum[2][tid] + colsum[3][tid]);
+            if (n < g.N) g.qpart[(long)blockIdx.z * g.q_batch + (long)n * g.n_mtiles + blockIdx.y] = (colsum[0][tid] + colsum[1][tid]) + (colsum[2][tid] + colsum[3][tid]);
         }
     }
 }
@@ -142,6 +145,48 @@ __global__ void geodetic_finish_kernel(GeoFinishArgs a)
     const double M = (double)(short)a.nsamp;
     const double norm = M * (2.0 * hp + 1.8378770664093453);
     a.logpts[(long)c * a.logpts_sc + a.out_col] = (-0.5) * (a.slog_pdet + norm + (1.0 / exp(hp * 2.0)) * quad);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dense-covariance seismic misfit as a GEMM (noise structures `non-toeplitz` / `import`: U_t is a full upper
+// triangle): residuals R[t][c][:] = data[t] - sum_chunks partial, Z_t = U_t R_t on the FP64 tensor cores
+// (batched over targets through blockIdx.z), then logpt per (chain, target).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) residual_from_partials_kernel(const double* __restrict__ partial, const double* __restrict__ data,
+                                                                      double* __restrict__ R, int B, int nt, int ns, int nchunk)
+{
+    const int c = blockIdx.x % B, t = blockIdx.x / B;
+    const double* pp = partial + ((long)c * nt + t) * nchunk * ns;
+    double* r = R + ((long)t * B + c) * ns;
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+        double s = pp[k];
+        for (int j = 1; j < nchunk; ++j) s += pp[(long)j * ns + k];
+        r[k] = data[(long)t * ns + k] - s;                                               // seismic.py:1332
+    }
+}
+
+struct SeisFinishArgs {
+    int B, nt, n_mtiles;
+    const double* qpart;                  // [nt, B, n_mtiles]
+    const double* slog_pdet; const int* nsamp; const int* hyper_idx;   // [nt]
+    const double* hyp; long hyp_sc;
+    const unsigned char* chain_bad;
+    double* logpts; long logpts_sc; int out_ofs;
+};
+
+__global__ void seismic_finish_kernel(SeisFinishArgs a)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)a.B * a.nt) return;
+    const int c = (int)(i % a.B), t = (int)(i / a.B);
+    double quad = 0.0;
+    for (int j = 0; j < a.n_mtiles; ++j) quad += a.qpart[((long)t * a.B + c) * a.n_mtiles + j];
+    const double hp = a.hyp[(long)c * a.hyp_sc + a.hyper_idx[t]];
+    const double M = (double)(short)a.nsamp[t];
+    const double norm = M * (2.0 * hp + 1.8378770664093453);
+    double lp = (-0.5) * (a.slog_pdet[t] + norm + (1.0 / exp(hp * 2.0)) * quad);
+    if (a.chain_bad && a.chain_bad[c]) lp = CUDART_NAN;
+    a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = lp;
 }
 
 }  // namespace beatgpu

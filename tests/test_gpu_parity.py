@@ -475,3 +475,60 @@ def test_eval_device_is_stream_ordered_with_torch():
         assert np.array_equal(got_like, ref_like)
         np.testing.assert_allclose(got_total, ref_like.sum(), rtol=1e-12)
     ev.close()
+
+
+@pytest.mark.parametrize("mode", ["mma", "simple"])
+@pytest.mark.parametrize("ns,B", [(130, 70), (40, 33), (64, 128)])
+def test_dense_covariance_misfit_gemm_path(mode, ns, B, monkeypatch):
+    """Full non-Toeplitz covariance (dense upper-triangular U): in the chunked path |U r|^2 of all chains is a batched
+    FP64 tensor-core GEMM per target ("mma") or one matvec per (chain, target) ("simple"); both equal the oracle."""
+    from beat_b200.engine import BatchedFFILogLike
+    monkeypatch.setenv("BEATGPU_GEO_MODE", mode)
+    monkeypatch.setenv("BEATGPU_STACK_MODE", "chunked")
+    monkeypatch.setenv("BEATGPU_CHUNK", "8")
+    prob = synthetic.make_problem(nt=3, subfaults=((4, 7, 2.0),), ns=ns, ndur=4, noise="dense", hp_specific=True, seed=71)
+    Q = synthetic.draw_chains(prob, B, seed=2)
+    ref = _oracle_logpts(prob, Q)
+    for store, rtol in (("float64", 1e-10), ("float32", 1e-5)):
+        ev = BatchedFFILogLike.from_problem(prob, store_dtype=store)
+        logpts, like = ev(Q)
+        np.testing.assert_allclose(logpts, ref, rtol=rtol)
+        Qbad = Q.copy()
+        Qbad[4, prob["offsets"]["time"]] = 1e4
+        Qbad[9, prob["offsets"]["nucleation_strike"]] = 1e3
+        with pytest.raises(IndexError):
+            ev(Qbad)
+        ev.close()
+    # a general (non-triangular) weight matrix, e.g. the QR fallback of chol_inverse, goes through the same path
+    rng = np.random.default_rng(0)
+    wm = prob["wavemaps"][0]
+    Ufull = wm["U"] + 0.01 * rng.standard_normal(wm["U"].shape) * np.abs(wm["U"]).max()
+    prob2 = dict(prob, wavemaps=[dict(wm, U=Ufull)])
+    ev = BatchedFFILogLike.from_problem(prob2, store_dtype="float64")
+    np.testing.assert_allclose(ev(Q)[0], _oracle_logpts(prob2, Q), rtol=1e-10)
+    ev.close()
+
+
+def test_mvn_chol_dense_weights_batched_gemm():
+    """multivariate_normal_chol with full (dense) weights and many chains: the tensor-core GEMM route of misfit_batch."""
+    import scipy.stats
+    import types
+    from beat_b200.covariance import Covariance
+    from beat_b200.ops import multivariate_normal_chol
+    rng = np.random.default_rng(12)
+    n_t, ns, B = 3, 150, 80
+    Cs = []
+    for i in range(n_t):
+        a = rng.random((ns, ns))
+        Cs.append((a.T.dot(a) + np.eye(ns) * 0.3) * 0.01)                   # recipe of test/test_covariance.py:72-74
+    covs = [Covariance(data=c) for c in Cs]
+    datasets = [types.SimpleNamespace(samples=ns, typ="any_P_Z", covariance=c) for c in covs]
+    res = rng.standard_normal((B, n_t, ns)) * 0.2
+    h = rng.uniform(0, 1, B)
+    got = multivariate_normal_chol(datasets, [c.chol_inverse for c in covs], {"h_any_P_Z": h}, res)
+    for b in range(0, B, 9):
+        for i in range(n_t):
+            ref = scipy.stats.multivariate_normal.logpdf(res[b, i], mean=np.zeros(ns), cov=Cs[i] * np.exp(2 * h[b]))
+            assert abs(got[b, i] - ref) <= 1e-8 * abs(ref)
+    ref_all = np.array([O.mvn_chol_logpts(res[b], [c.chol_inverse for c in covs], [c.log_pdet for c in covs], [ns] * n_t, h[b]) for b in range(B)])
+    np.testing.assert_allclose(got, ref_all, rtol=1e-11)
