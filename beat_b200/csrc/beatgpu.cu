@@ -429,7 +429,6 @@ const char* beatgpu_last_error(const beatgpu_ctx* ctx) { return ctx ? ctx->err.c
 
 int beatgpu_ctx_create(int device, beatgpu_ctx** out)
 {
-    beatgpu_ctx* ctx = nullptr;
     if (!out) return fail(nullptr, BEATGPU_E_ARG, "out is NULL");
     *out = nullptr;
     int ndev = 0;
@@ -457,7 +456,6 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_STACK_MODE")) c->stack_mode = (strcmp(e, "fused") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_GEO_MODE")) c->geo_mode = (strcmp(e, "simple") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) c->chunk_patches = v; }
-    (void)ctx;
     *out = c;
     return BEATGPU_OK;
 }

@@ -35,12 +35,10 @@ class BatchedFFILogLike:
     def __init__(self, device=0):
         self.ctx = Context(device)
         self.device = device
-        self.prob_meta = None
         self.wmap_ids = []
         self._wm_shapes = []
         self.n_params = 0
         self.npatches = 0
-        self._torch_bufs = {}
 
     # ------------------------------------------------------------------ construction
     @classmethod

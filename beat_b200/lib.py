@@ -140,7 +140,6 @@ class Context:
             raise BeatGpuError(rc, self._lib.beatgpu_last_error(None).decode())
         self._h = h
         self.device = int(device)
-        self._keep = []
 
     def close(self):
         if getattr(self, "_h", None):

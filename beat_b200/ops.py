@@ -40,16 +40,6 @@ except Exception:  # pragma: no cover - exercised on boxes without pytensor
             return out[0][0] if len(out) == 1 else [o[0] for o in out]
 
 
-_default_ctx = {}
-
-
-def default_context(device=0):
-    """One shared context per (process, device) for the stand-alone Ops."""
-    if device not in _default_ctx:
-        _default_ctx[device] = Context(device)
-    return _default_ctx[device]
-
-
 class Sweeper(_OpBase):
     """GPU implementation of the fast-sweeping Op (reference: beat/pytensorf.py:410-503).
 
