@@ -511,6 +511,23 @@ int beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream, int external)
     return BEATGPU_OK;
 }
 
+int beatgpu_host_register(beatgpu_ctx* ctx, void* ptr, int64_t bytes)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (!ptr || bytes <= 0) return fail(ctx, BEATGPU_E_ARG, "host_register: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault));
+    return BEATGPU_OK;
+}
+
+int beatgpu_host_unregister(beatgpu_ctx* ctx, void* ptr)
+{
+    if (!ctx) return BEATGPU_E_ARG;
+    if (!ptr) return fail(ctx, BEATGPU_E_ARG, "host_unregister: NULL");
+    CK(cudaHostUnregister(ptr));
+    return BEATGPU_OK;
+}
+
 int beatgpu_device_info(beatgpu_ctx* ctx, int* n_sm, char* name, int name_len)
 {
     if (!ctx) return BEATGPU_E_ARG;

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "beatgpu_last_error": (C.c_char_p, [_P]),
     "beatgpu_sync": (C.c_int, [_P]),
     "beatgpu_set_stream": (C.c_int, [_P, _P, C.c_int]),
+    "beatgpu_host_register": (C.c_int, [_P, _P, C.c_int64]),
+    "beatgpu_host_unregister": (C.c_int, [_P, _P]),
     "beatgpu_device_info": (C.c_int, [_P, C.POINTER(C.c_int), C.c_char_p, C.c_int]),
     "beatgpu_set_fault": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_set_layout": (C.c_int, [_P, C.POINTER(Layout), _P]),
@@ -168,6 +170,16 @@ class Context:
     def set_stream(self, cuda_stream_ptr, external=True):
         """external=True: enqueue on the given CUDA stream handle (0 = default stream); False: private stream."""
         self._check(self._lib.beatgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr or 0), 1 if external else 0))
+
+    def pin(self, array):
+        """Page-lock a numpy array in place (cudaHostRegister) for full-rate H2D/D2H in the host-pointer entries."""
+        if not array.flags["C_CONTIGUOUS"]:
+            raise ValueError("only C-contiguous arrays can be pinned")
+        self._check(self._lib.beatgpu_host_register(self._h, array.ctypes.data_as(C.c_void_p), array.nbytes))
+        return array
+
+    def unpin(self, array):
+        self._check(self._lib.beatgpu_host_unregister(self._h, array.ctypes.data_as(C.c_void_p)))
 
     def device_info(self):
         n = C.c_int()

@@ -63,6 +63,11 @@ int         beatgpu_sync(beatgpu_ctx* ctx);                 /* cudaStreamSynchro
  * the default stream) so the library's kernels are ordered with the caller's work on that stream;
  * external == 0: go back to a private non-blocking stream (cuda_stream ignored).                       */
 int         beatgpu_set_stream(beatgpu_ctx* ctx, void* cuda_stream, int external);
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so the host-pointer entries copy it at full PCIe rate;
+ * a sampler registers its parameter / output arrays once and reuses them every step.  The memory stays the
+ * caller's; unregister before freeing it.                                                                   */
+int         beatgpu_host_register(beatgpu_ctx* ctx, void* ptr, int64_t bytes);
+int         beatgpu_host_unregister(beatgpu_ctx* ctx, void* ptr);
 /* number of SMs, device name; for sizing/reporting */
 int         beatgpu_device_info(beatgpu_ctx* ctx, int* n_sm, char* name, int name_len);
 

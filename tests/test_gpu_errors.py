@@ -48,3 +48,22 @@ def test_call_order_and_argument_errors():
     with pytest.raises(ValueError, match="unknown wavemap"):
         c.upload_data(7, np.zeros((1, 8)))
     c.close()
+
+
+def test_host_register_roundtrip():
+    from beat_b200 import synthetic
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=3, subfaults=((4, 5, 2.0),), ns=20, ndur=4, seed=2)
+    Q = synthetic.draw_chains(prob, 10, seed=1)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    ref, ref_like = ev(Q)
+    Qp = ev.ctx.pin(np.ascontiguousarray(Q.copy()))
+    logpts = ev.ctx.pin(np.empty((10, ev.n_out)))
+    like = ev.ctx.pin(np.empty(10))
+    ev.ctx.ffi_loglike_batch(Qp, logpts, like)
+    assert np.array_equal(logpts, ref) and np.array_equal(like, ref_like)
+    for a in (Qp, logpts, like):
+        ev.ctx.unpin(a)
+    with pytest.raises(Exception):
+        ev.ctx.unpin(Qp)                 # not registered any more
+    ev.close()
