@@ -87,6 +87,9 @@ class BatchedFFILogLike:
             lp = prob["laplacian"]
             ctx.set_laplacian(lp["L"], lp["sdet"], lp["hyper_idx"])
         self.n_out = ctx.n_outputs()
+        esz = 4 if code == F32 else 8
+        self._bytes_per_eval = sum(wm["nt"] * prob["npatches"] * wm["ns"] * (4 if wm["interpolation"] == "multilinear" else 1)
+                                   * len(self.slip_vars) * esz for wm in prob["wavemaps"])
         return self
 
     def alloc_library(self, wmap_index, slipvar_index, dims, dur_min, dur_step, st_min, st_step):
@@ -144,6 +147,22 @@ class BatchedFFILogLike:
         wm = self._wm_shapes[wmap_index]
         out = self.ctx.ffi_synthetics_batch(self.wmap_ids[wmap_index], Q, wm[0], wm[1])
         return out[0] if single else out
+
+    def stats(self, B=None):
+        """Counters for logging (the reference only has wall-clock debug lines, beat/models/seismic.py:1229,1345-1346):
+        kernels launched so far, duration of the last stacking pass and -- given the batch size -- the achieved
+        algorithmic GB/s of that pass (SURVEY 8d bytes: nt*np*ns*K*nvar*sizeof(gf) per evaluation)."""
+        out = {"launches": self.ctx.launch_count()}
+        try:
+            ms = self.ctx.last_stack_ms()
+        except Exception:
+            return out
+        out["last_stack_ms"] = ms
+        if B:
+            out["evals_per_s_stack"] = B / (ms / 1e3)
+            if getattr(self, "_bytes_per_eval", None):
+                out["algorithmic_GBps"] = self._bytes_per_eval * B / (ms / 1e3) / 1e9
+        return out
 
     def starttimes(self, B):
         return self.ctx.get_starttimes(B, self.npatches)

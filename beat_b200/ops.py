@@ -190,7 +190,7 @@ class SeismicGFLibrary(object):
         return out[0] if single else out
 
 
-def multivariate_normal_chol(datasets, weights, hyperparams, residuals, hp_specific=False, device=0, _cache={}):
+def multivariate_normal_chol(datasets, weights, hyperparams, residuals, hp_specific=False, device=0):
     """Batched GPU ``multivariate_normal_chol`` (reference: beat/models/distributions.py:72-140).
 
     datasets: objects with ``.samples``, ``.typ`` and ``.covariance.slog_pdet`` / ``.covariance.log_pdet`` as in the
