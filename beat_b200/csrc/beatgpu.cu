@@ -933,6 +933,48 @@ int beatgpu_stack_batch(beatgpu_ctx* ctx, int wmap_id, int B, int nvar, const do
     return check_violations(ctx, "stack_batch");
 }
 
+static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* d_resid, const double* d_hyp, int n_hypers, double* d_logpts)
+{
+    int rc;
+    if (w.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && B >= 32) {
+        // dense weights: Z_t = U_t R_t for all chains on the FP64 tensor cores, straight from the caller's layout
+        const int mt = (w.ns + kGemmTile - 1) / kGemmTile;
+        if ((rc = ensure_tmp(ctx, 5, (size_t)w.nt * B * mt * sizeof(double)))) return rc;
+        GemmArgs g;
+        memset(&g, 0, sizeof(g));
+        g.M = w.ns; g.N = B; g.K = w.ns; g.n_parts = 1;
+        g.A[0] = w.d_W; g.a_sm = 1; g.a_sk = w.ns; g.a_batch = (long)w.ns * w.ns;
+        g.B[0] = d_resid; g.b_sk = 1; g.b_sn[0] = (long)w.nt * w.ns; g.b_batch = w.ns;   // resid[c][t][k]
+        g.upper = w.dense_upper;
+        g.qpart = (double*)ctx->d_tmp[5]; g.n_mtiles = mt; g.q_batch = (long)B * mt;
+        dim3 grid((B + kGemmTile - 1) / kGemmTile, mt, w.nt);
+        dgemm_tile_kernel<1><<<grid, kGemmThreads, 0, ctx->stream>>>(g);
+        CKL();
+        SeisFinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.B = B; f.nt = w.nt; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];
+        f.slog_pdet = w.d_slog_pdet; f.nsamp = w.d_nsamp; f.hyper_idx = w.d_hyper_idx;
+        f.hyp = d_hyp; f.hyp_sc = n_hypers; f.chain_bad = nullptr;
+        f.logpts = d_logpts; f.logpts_sc = w.nt; f.out_ofs = 0;
+        seismic_finish_kernel<<<(unsigned)(((long)B * w.nt + 127) / 128), 128, 0, ctx->stream>>>(f);
+        CKL();
+    } else {
+        MisfitArgs a;
+        memset(&a, 0, sizeof(a));
+        a.B = B; a.nt = w.nt; a.ns = w.ns;
+        a.resid = d_resid;
+        a.hyp = d_hyp; a.hyp_sc = n_hypers; a.hyper_idx = w.d_hyper_idx;
+        a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
+        a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
+        a.logpts = d_logpts; a.logpts_sc = w.nt; a.out_ofs = 0;
+        const size_t smem = (size_t)w.ns * sizeof(double);
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
+        CKL();
+    }
+    return BEATGPU_OK;
+}
+
 int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* residuals, const double* hypers, int n_hypers,
                          double* logpts)
 {
@@ -944,45 +986,19 @@ int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* res
     if ((rc = ensure_tmp(ctx, 0, b_r)) || (rc = ensure_tmp(ctx, 1, b_h)) || (rc = ensure_tmp(ctx, 2, b_o))) return rc;
     CK(cudaMemcpyAsync(ctx->d_tmp[0], residuals, b_r, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tmp[1], hypers, b_h, cudaMemcpyHostToDevice, ctx->stream));
-    if (w.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && B >= 32) {
-        // dense weights: Z_t = U_t R_t for all chains on the FP64 tensor cores, straight from the caller's layout
-        const int mt = (w.ns + kGemmTile - 1) / kGemmTile;
-        if ((rc = ensure_tmp(ctx, 5, (size_t)w.nt * B * mt * sizeof(double)))) return rc;
-        GemmArgs g;
-        memset(&g, 0, sizeof(g));
-        g.M = w.ns; g.N = B; g.K = w.ns; g.n_parts = 1;
-        g.A[0] = w.d_W; g.a_sm = 1; g.a_sk = w.ns; g.a_batch = (long)w.ns * w.ns;
-        g.B[0] = (const double*)ctx->d_tmp[0]; g.b_sk = 1; g.b_sn[0] = (long)w.nt * w.ns; g.b_batch = w.ns;   // resid[c][t][k]
-        g.upper = w.dense_upper;
-        g.qpart = (double*)ctx->d_tmp[5]; g.n_mtiles = mt; g.q_batch = (long)B * mt;
-        dim3 grid((B + kGemmTile - 1) / kGemmTile, mt, w.nt);
-        dgemm_tile_kernel<1><<<grid, kGemmThreads, 0, ctx->stream>>>(g);
-        CKL();
-        SeisFinishArgs f;
-        memset(&f, 0, sizeof(f));
-        f.B = B; f.nt = w.nt; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];
-        f.slog_pdet = w.d_slog_pdet; f.nsamp = w.d_nsamp; f.hyper_idx = w.d_hyper_idx;
-        f.hyp = (const double*)ctx->d_tmp[1]; f.hyp_sc = n_hypers; f.chain_bad = nullptr;
-        f.logpts = (double*)ctx->d_tmp[2]; f.logpts_sc = w.nt; f.out_ofs = 0;
-        seismic_finish_kernel<<<(unsigned)(((long)B * w.nt + 127) / 128), 128, 0, ctx->stream>>>(f);
-        CKL();
-    } else {
-        MisfitArgs a;
-        memset(&a, 0, sizeof(a));
-        a.B = B; a.nt = w.nt; a.ns = w.ns;
-        a.resid = (const double*)ctx->d_tmp[0];
-        a.hyp = (const double*)ctx->d_tmp[1]; a.hyp_sc = n_hypers; a.hyper_idx = w.d_hyper_idx;
-        a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
-        a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
-        a.logpts = (double*)ctx->d_tmp[2]; a.logpts_sc = w.nt; a.out_ofs = 0;
-        const size_t smem = (size_t)w.ns * sizeof(double);
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
-        CKL();
-    }
+    if ((rc = misfit_batch_core(ctx, w, B, (const double*)ctx->d_tmp[0], (const double*)ctx->d_tmp[1], n_hypers, (double*)ctx->d_tmp[2]))) return rc;
     CK(cudaMemcpyAsync(logpts, ctx->d_tmp[2], b_o, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return BEATGPU_OK;
+}
+
+int beatgpu_misfit_batch_dev(beatgpu_ctx* ctx, int wmap_id, int B, const double* residuals_dev, const double* hypers_dev,
+                             int n_hypers, double* logpts_dev)
+{
+    GET_WMAP(wmap_id);
+    if (B <= 0 || !residuals_dev || !hypers_dev || n_hypers <= 0 || !logpts_dev) return fail(ctx, BEATGPU_E_ARG, "misfit_batch_dev: bad arguments");
+    if (w.misfit_mode < 0) return fail(ctx, BEATGPU_E_NOTREADY, "misfit_batch_dev: weights not uploaded (update_weights)");
+    return misfit_batch_core(ctx, w, B, residuals_dev, hypers_dev, n_hypers, logpts_dev);
 }
 
 // rupture onset times for all chains / subfaults into ctx->d_t0 (seismic.py:1253-1272)

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "beatgpu_fast_sweep_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "beatgpu_stack_batch": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P]),
     "beatgpu_misfit_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
+    "beatgpu_misfit_batch_dev": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, C.c_int, _P]),
     "beatgpu_ffi_loglike_batch": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_ffi_loglike_batch_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_ffi_synthetics_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
@@ -291,6 +292,10 @@ class Context:
         out = np.empty((B, nt))
         self._check(self._lib.beatgpu_misfit_batch(self._h, wmap, B, _ptr(r), _ptr(h), h.shape[1], _ptr(out)))
         return out
+
+    def misfit_batch_dev(self, wmap, B, resid_ptr, hyp_ptr, n_hypers, logpts_ptr):
+        self._check(self._lib.beatgpu_misfit_batch_dev(self._h, wmap, int(B), C.c_void_p(resid_ptr), C.c_void_p(hyp_ptr),
+                                                       int(n_hypers), C.c_void_p(logpts_ptr)))
 
     def ffi_loglike_batch(self, q, logpts=None, like=None):
         """Host-pointer entry (copies in and out, synchronises).  q [B, n_params] float64 C-contiguous."""

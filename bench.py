@@ -497,6 +497,48 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_c2_llk(args):
+    """For the record (not the BASELINE metric): the log-likelihood stage of config 2 (DC point source, 32 stations x 3
+    components x 2048 samples, Toeplitz covariance, 2000 chains) with residuals resident in HBM.  The geometry-mode
+    forward model itself lives in pyrocko and is out of scope."""
+    import torch
+    from beat_b200.covariance import Covariance, exponential_data_covariance
+    from beat_b200.lib import Context
+    dev = torch.device("cuda", 0)
+    nt, ns, B = 96, 2048, args.chains if args.chains != 4000 else 2000
+    ctx = Context(0)
+    wid = ctx.add_wavemap(nt, ns, "nearest_neighbor", None, np.zeros(nt, np.int32), np.full(nt, ns, np.int32))
+    cov = Covariance(data=exponential_data_covariance(ns, 0.5, 2.0) * 0.05 ** 2)
+    U = np.broadcast_to(cov.chol_inverse, (nt, ns, ns)) if args.noise != "dense" else None
+    if args.noise == "dense":
+        rng = np.random.default_rng(0)
+        a = rng.random((ns, ns))
+        cov = Covariance(data=(a.T.dot(a) + np.eye(ns) * 0.3) * 1e-3)
+        U = np.broadcast_to(cov.chol_inverse, (nt, ns, ns))
+    ctx.update_weights(wid, np.ascontiguousarray(U), np.full(nt, cov.log_pdet))
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream, external=True)
+    res = torch.randn((B, nt, ns), dtype=torch.float64, device=dev) * 0.05
+    hyp = torch.zeros((B, 1), dtype=torch.float64, device=dev)
+    out = torch.empty((B, nt), dtype=torch.float64, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(args.warmup):
+        ctx.misfit_batch_dev(wid, B, res.data_ptr(), hyp.data_ptr(), 1, out.data_ptr())
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        ctx.misfit_batch_dev(wid, B, res.data_ptr(), hyp.data_ptr(), 1, out.data_ptr())
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    bytes_step = B * nt * ns * 8
+    print(json.dumps({"metric": "loglike evals/sec (C2 shapes: 96 datasets x 2048 samples, %s covariance; llk stage only, not the BASELINE metric)" % args.noise,
+                      "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                      "config": {"workload": "C2 llk stage", "chains_per_gpu": B},
+                      "roofline": {"bound": "hbm" if args.noise != "dense" else "tensor(f64)", "achieved": bytes_step / (ms / 1e3) / 1e9, "unit": "GB/s",
+                                   "algorithmic_bytes_per_launch": bytes_step}}))
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -510,12 +552,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="exponential", choices=["exponential", "variance", "dense"],
                     help="data covariance structure (exponential = BASELINE config; dense = full non-Toeplitz, for the record)")
-    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"], help="c3 = BASELINE.json metric; c4/c5 for the record")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5", "c2llk"], help="c3 = BASELINE.json metric; c4/c5 for the record")
     args = ap.parse_args()
     global CONFIG, NOISE
     CONFIG, NOISE = args.config, args.noise
     args.warmup = max(args.warmup, 3)
-    if args.impl == "reference":
+    if args.config == "c2llk":
+        run_c2_llk(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

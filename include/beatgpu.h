@@ -191,6 +191,11 @@ int beatgpu_stack_batch(beatgpu_ctx* ctx, int wmap_id, int B, int n_slipvars_use
 int beatgpu_misfit_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* residuals,
                          const double* hypers, int n_hypers, double* logpts);
 
+/* Same with DEVICE pointers, enqueued on the ctx stream without synchronisation (e.g. the log-likelihood of a
+ * geometry-mode problem whose synthetics are produced elsewhere on the device).                          */
+int beatgpu_misfit_batch_dev(beatgpu_ctx* ctx, int wmap_id, int B, const double* residuals_dev,
+                             const double* hypers_dev, int n_hypers, double* logpts_dev);
+
 /* The fused evaluation: replaces one call of the compiled logp_forw_func(q)
  * (beat/sampler/base.py:598-615; graph of seismic.py:1253-1349 [+ geodetic.py:1065-1084,
  * laplacian.py:98-139]) for each of B chains: q [B, n_params] -> logpts [B, n_out] and

@@ -532,3 +532,32 @@ def test_mvn_chol_dense_weights_batched_gemm():
             assert abs(got[b, i] - ref) <= 1e-8 * abs(ref)
     ref_all = np.array([O.mvn_chol_logpts(res[b], [c.chol_inverse for c in covs], [c.log_pdet for c in covs], [ns] * n_t, h[b]) for b in range(B)])
     np.testing.assert_allclose(got, ref_all, rtol=1e-11)
+
+
+def test_misfit_batch_dev_long_traces():
+    """Config-2 trace length (2048 samples, Toeplitz covariance -> banded weights): device-pointer misfit entry equals
+    the host entry and the oracle."""
+    import torch
+    from beat_b200.covariance import Covariance, exponential_data_covariance
+    from beat_b200.lib import Context
+    rng = np.random.default_rng(3)
+    nt, ns, B = 3, 2048, 5
+    covs = [Covariance(data=exponential_data_covariance(ns, 0.5, 2.0 + i) * 0.05 ** 2) for i in range(nt)]
+    U = np.stack([c.chol_inverse for c in covs])
+    lp = np.array([c.log_pdet for c in covs])
+    ctx = Context(0)
+    wid = ctx.add_wavemap(nt, ns, "nearest_neighbor", None, np.arange(nt, dtype=np.int32), np.full(nt, ns, np.int32))
+    ctx.update_weights(wid, U, lp)
+    res = rng.standard_normal((B, nt, ns)) * 0.05
+    hyp = rng.uniform(0, 1, (B, nt))
+    host = ctx.misfit_batch(wid, res, hyp)
+    for b in range(B):
+        ref = O.mvn_chol_logpts(res[b], U, lp, [ns] * nt, hyp[b])
+        np.testing.assert_allclose(host[b], ref, rtol=1e-9)
+    dev = torch.device("cuda", 0)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream, external=True)
+    r_d, h_d = torch.from_numpy(res).to(dev), torch.from_numpy(hyp).to(dev)
+    out = torch.empty((B, nt), dtype=torch.float64, device=dev)
+    ctx.misfit_batch_dev(wid, B, r_d.data_ptr(), h_d.data_ptr(), nt, out.data_ptr())
+    assert np.array_equal(out.cpu().numpy(), host)
+    ctx.close()
