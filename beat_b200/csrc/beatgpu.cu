@@ -132,9 +132,11 @@ int fail(beatgpu_ctx* c, int code, const char* fmt, ...)
 #define CK(call)                                                                                      \
     do {                                                                                              \
         cudaError_t e__ = (call);                                                                     \
-        if (e__ != cudaSuccess)                                                                       \
+        if (e__ != cudaSuccess) {                                                                     \
+            (void)cudaGetLastError(); /* clear the (non-sticky) error so later launch checks are not poisoned */ \
             return fail(ctx, BEATGPU_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
                         __FILE__, __LINE__);                                                          \
+        }                                                                                             \
     } while (0)
 
 #define CKL()                                                                                          \

@@ -66,4 +66,7 @@ def test_host_register_roundtrip():
         ev.ctx.unpin(a)
     with pytest.raises(Exception):
         ev.ctx.unpin(Qp)                 # not registered any more
+    # a failed runtime call must not poison later launches (the CUDA last-error state is cleared)
+    again, _ = ev(Q)
+    assert np.array_equal(again, ref)
     ev.close()
