@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(kStackThreads) misfit_kernel(MisfitArgs a)
         }
     } else {
         const double* r = a.resid + ((long)c * a.nt + t) * ns;
-        for (int k = tid; k < ns; k += kStackThreads) resid[k] = r[k];
+#pragma unroll 8
+        for (int k = tid; k < ns; k += kStackThreads) resid[k] = __ldg(r + k);      // several loads in flight per thread
     }
     __syncthreads();
     double q = 0.0;
