@@ -238,3 +238,82 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         torch.distributed.all_reduce(n_evals)
     return dict(population=q_all, likelihoods=like_all, logpts=logpts_all, betas=betas, n_stages=stage,
                 n_evals=int(n_evals.item()), acceptance=acc_hist)
+
+
+def pt_betas(n_chains, n_chains_posterior, t_scale):
+    """Temperature ladder of the reference's ``TemperingManager.update_betas`` (beat/sampler/pt.py:179-221):
+    ``n_chains_posterior`` chains at beta = 1, the others at beta = 1 / t_scale**k, k = 1.."""
+    n_temp = n_chains - n_chains_posterior
+    return np.concatenate([np.ones(n_chains_posterior), 1.0 / np.power(t_scale, np.arange(1, n_temp + 1))])
+
+
+def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_interval=(10, 15), n_chains_posterior=1,
+              t_scale=1.2, beta_tune_interval=None, proposal_cov=None, tune_interval=50, seed=0, initial_population=None,
+              record_every=1):
+    """Lock-step parallel tempering with a batched evaluator (restating beat/sampler/pt.py:100-469,472-704 without MPI).
+
+    The reference runs one Metropolis chain per MPI worker at its own beta, lets each run a random number of steps
+    drawn from ``swap_interval`` and has the master propose a state swap between two finished workers with
+    ``alpha = (beta2 - beta1) * (llk1 - llk2)`` (pt.py:428-455), counting acceptances per pair and re-scaling the
+    temperature ladder every ``beta_tune_interval`` samples.  Here all chains advance together (one batched evaluation
+    per step); after each interval the chains are paired at random and every pair proposes a swap with the same rule.
+    Returns the recorded samples of the beta = 1 chains."""
+    import torch
+    device = device if device is not None else torch.device("cpu")
+    rng = np.random.default_rng(seed)
+    lower = np.asarray(lower, dtype=np.float64)
+    upper = np.asarray(upper, dtype=np.float64)
+    n_params = lower.size
+    mh = BatchedMetropolis(evaluator, lower, upper, n_chains, device=device, tune=True, tune_interval=tune_interval, seed=seed * 7919 + 1)
+    if proposal_cov is None:
+        proposal_cov = np.diag(((upper - lower) * 0.05) ** 2)
+    mh.set_proposal_covariance(proposal_cov)
+    betas = pt_betas(n_chains, n_chains_posterior, t_scale)
+    mh.beta = torch.as_tensor(betas, device=device)
+    pop = rng.uniform(lower, upper, (n_chains, n_params)) if initial_population is None else np.array(initial_population, dtype=np.float64)
+    q = torch.as_tensor(pop, device=device).contiguous()
+    logpts, like = mh.initial_llk(q)
+
+    recorded, rec_like = [], []
+    n_swaps = n_acc = 0
+    since_tune_swaps = since_tune_acc = 0
+    done = 0
+    scales = [t_scale]
+    while done < n_samples:
+        draws = int(rng.integers(swap_interval[0], swap_interval[1]))        # pt.py:146-149 (DiscreteBoundedUniform)
+        draws = min(draws, n_samples - done)
+        for i in range(draws):
+            q, logpts, like, _ = mh.step(q, logpts, like)
+            if (done + i) % record_every == 0:
+                recorded.append(q[:n_chains_posterior].clone())
+                rec_like.append(like[:n_chains_posterior].clone())
+        done += draws
+        # swap proposals between randomly paired chains (pt.py:428-455)
+        perm = rng.permutation(n_chains)
+        a = torch.as_tensor(perm[0: 2 * (n_chains // 2): 2].copy(), device=device)
+        b = torch.as_tensor(perm[1: 2 * (n_chains // 2): 2].copy(), device=device)
+        beta_t = mh.beta
+        alpha = (beta_t[b] - beta_t[a]) * (like[a] - like[b])
+        u = torch.as_tensor(rng.random(a.numel()), device=device)
+        acc = torch.log(u) < alpha
+        ia, ib = a[acc], b[acc]
+        if ia.numel():
+            q = q.clone()
+            logpts, like = logpts.clone(), like.clone()
+            qa, la, lpa = q[ia].clone(), like[ia].clone(), logpts[ia].clone()
+            q[ia], like[ia], logpts[ia] = q[ib], like[ib], logpts[ib]
+            q[ib], like[ib], logpts[ib] = qa, la, lpa
+        k = int(acc.sum())
+        n_swaps += a.numel(); n_acc += k
+        since_tune_swaps += a.numel(); since_tune_acc += k
+        if beta_tune_interval and since_tune_swaps >= beta_tune_interval:
+            rate = since_tune_acc / float(since_tune_swaps)
+            t_scale = float(np.clip(float(tune_scale(torch.tensor([t_scale], dtype=torch.float64),
+                                                      torch.tensor([rate], dtype=torch.float64))[0]), 1.01, 2.0))   # pt.py:126-127
+            mh.beta = torch.as_tensor(pt_betas(n_chains, n_chains_posterior, t_scale), device=device)
+            scales.append(t_scale)
+            since_tune_swaps = since_tune_acc = 0
+    samples = torch.stack(recorded).reshape(-1, n_params).cpu().numpy()
+    return dict(samples=samples, likelihoods=torch.stack(rec_like).reshape(-1).cpu().numpy(), betas=np.asarray(mh.beta.cpu()),
+                swap_acceptance=n_acc / max(1, n_swaps), t_scales=scales, n_evals=mh.n_evals,
+                population=q.cpu().numpy(), population_likelihoods=like.cpu().numpy())

@@ -77,3 +77,19 @@ def test_tune_scale_table():
     s = torch.ones(6, dtype=torch.float64)
     acc = torch.tensor([0.0005, 0.03, 0.1, 0.3, 0.6, 0.99], dtype=torch.float64)
     np.testing.assert_allclose(S.tune_scale(s, acc).numpy(), [0.1, 0.5, 0.9, 1.0, 1.1, 10.0])
+
+
+def test_pt_two_gaussians_like_reference_test():
+    """Lock-step parallel tempering on the toy posterior of test/test_pt.py (same two-Gaussian mixture): the beta = 1
+    chains visit both modes in the right proportion (w1 = 0.1) and recover |x| ~ 0.5."""
+    ev, mu1 = _two_gaussians_evaluator()
+    n = 4
+    out = S.pt_sample(ev, -2.0 * np.ones(n), 2.0 * np.ones(n), n_chains=16, n_samples=6000, swap_interval=(10, 15),
+                      n_chains_posterior=4, t_scale=1.6, beta_tune_interval=200, seed=5)
+    x = out["samples"][len(out["samples"]) // 5:]                      # drop burn-in
+    np.testing.assert_allclose(np.abs(x).mean(axis=0), mu1, rtol=0.0, atol=0.05)
+    frac_pos = (x[:, 0] > 0).mean()
+    assert 0.02 < frac_pos < 0.35, frac_pos
+    assert 0.0 < out["swap_acceptance"] <= 1.0
+    assert out["betas"][0] == 1.0 and np.all(np.diff(out["betas"][3:]) < 0)
+    np.testing.assert_allclose(S.pt_betas(5, 2, 2.0), [1, 1, 0.5, 0.25, 0.125])
