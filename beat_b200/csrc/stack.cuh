@@ -480,9 +480,9 @@ gf_stack_chunk_kernel(ChunkArgs ca)
         const int nvec = (wlen * (int)sizeof(T) + 15) / 16;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (sizeof(T) == 4) {
-            // rows of PF patches in flight per lane.  Measured at C3: PF = 2 beats PF = 8 for nearest neighbour too
-            // (789 k vs 732 k evals/s): occupancy (register count) matters more than per-lane depth.
-            constexpr int PF = 2;
+            // rows of PF patches in flight per lane.  Measured at C3, nearest neighbour: PF = 2 / 4 / 8 -> 789 k / 840 k /
+            // 732 k evals/s (depth vs registers/occupancy); multilinear already has 8*NVAR loads per patch.
+            constexpr int PF = (K == 1) ? 4 : 2;
             const bool active = lane < nvec;
             for (int i = 0; i < pn; i += PF) {
                 float4 g[PF][K * NVAR];
