@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(kStackThreads) misfit_kernel(MisfitArgs a)
         // synth = sum of the patch-chunk partials in fixed chunk order (deterministic); residual = data - synth
         const double* pp = a.partial + ((long)c * a.nt + t) * a.nchunk * ns;
         for (int k = tid; k < ns; k += kStackThreads) {
-            double s = pp[k];
-            for (int j = 1; j < a.nchunk; ++j) s += pp[(long)j * ns + k];
+            double s = __ldcs(pp + k);
+            for (int j = 1; j < a.nchunk; ++j) s += __ldcs(pp + (long)j * ns + k);
             resid[k] = a.data[(long)t * ns + k] - s;                                     // seismic.py:1332
         }
     } else {
@@ -545,7 +545,8 @@ gf_stack_chunk_kernel(ChunkArgs ca)
 #pragma unroll
             for (int e = 0; e < 4; e += 2) {
                 const int sidx = slot_sample<T>(lane, e);
-                if (sidx + 1 < wlen) *reinterpret_cast<double2*>(out + s0 + sidx) = make_double2(acc[e], acc[e + 1]);
+                // streaming store: the partials are read once by the misfit pass and must not evict library rows from L2
+                if (sidx + 1 < wlen) __stcs(reinterpret_cast<double2*>(out + s0 + sidx), make_double2(acc[e], acc[e + 1]));
                 else if (sidx < wlen) out[s0 + sidx] = acc[e];
             }
         } else {
