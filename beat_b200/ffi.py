@@ -110,3 +110,49 @@ def save_gf_library(outdir, traces, tmins, component="uparr", wavename="any_P", 
         body = yaml.safe_dump(cfg, default_flow_style=False, sort_keys=False)
         f.write(body.replace("wave_config:\n", "wave_config: !beat.WaveformFitConfig\n"))
     return prefix
+
+
+def discover_seismic_libraries(gfpath, slip_vars, crust_ind=0):
+    """Find the seismic libraries of a project's ``<project>/ffi/linear_gfs`` directory (reference naming:
+    ``seismic_<component>_<mapid>_<crust_ind>``, beat/ffi/base.py:157-158, beat/models/seismic.py:1168-1208).
+
+    Returns an ordered list of wavemaps: ``[(mapid, {component: prefix})]`` for every mapid that has all ``slip_vars``."""
+    import glob
+    import re
+    found = {}
+    for path in sorted(glob.glob(os.path.join(gfpath, "seismic_*_%i.yaml" % crust_ind))):
+        prefix = os.path.basename(path)[: -len(".yaml")]
+        for comp in slip_vars:
+            m = re.match(r"^seismic_%s_(.+)_%i$" % (re.escape(comp), crust_ind), prefix)
+            if m:
+                found.setdefault(m.group(1), {})[comp] = prefix
+    return [(mapid, comps) for mapid, comps in sorted(found.items()) if all(c in comps for c in slip_vars)]
+
+
+def wavemaps_from_directory(gfpath, slip_vars, interpolation="multilinear", crust_ind=0):
+    """Build the ``prob['wavemaps']`` entries (library part) of :class:`beat_b200.engine.BatchedFFILogLike` straight from
+    the reference's library files: traces stay memory-mapped and are streamed to HBM at upload.  The caller adds the
+    per-wavemap ``data``, ``U``, ``slog_pdet``, ``nsamples``, ``hyper_idx`` and ``station_idx`` (they come from the
+    reference's datasets / Covariance objects)."""
+    out = []
+    for mapid, comps in discover_seismic_libraries(gfpath, slip_vars, crust_ind):
+        cfg0, G, tmins = None, {}, None
+        for comp in slip_vars:
+            cfg = read_library_config(os.path.join(gfpath, comps[comp] + ".yaml"))
+            G[comp] = np.load(os.path.join(gfpath, comps[comp] + ".traces.npy"), mmap_mode="r", allow_pickle=False)
+            if tuple(G[comp].shape) != tuple(int(x) for x in cfg["dimensions"]):
+                raise GFLibraryError("%s: traces shape %s != config dimensions %s" % (comps[comp], G[comp].shape, cfg["dimensions"]))
+            if cfg0 is None:
+                cfg0 = cfg
+                tmins = np.load(os.path.join(gfpath, comps[comp] + ".times.npy"), allow_pickle=False)
+            else:
+                for key in ("dimensions", "duration_min", "duration_sampling", "starttime_min", "starttime_sampling"):
+                    if cfg[key] != cfg0[key]:
+                        raise GFLibraryError("libraries of wavemap %s differ in %s" % (mapid, key))
+        nt, _, ndur, nst, ns = (int(x) for x in cfg0["dimensions"])
+        out.append(dict(mapid=mapid, nt=nt, ns=ns, ndur=ndur, nst=nst, G=G, tmins=tmins, interpolation=interpolation,
+                        dur_min=float(cfg0["duration_min"]), dur_step=float(cfg0["duration_sampling"]),
+                        st_min=float(cfg0["starttime_min"]), st_step=float(cfg0["starttime_sampling"])))
+    if not out:
+        raise GFLibraryError("no seismic GF libraries for %s found in %s" % (list(slip_vars), gfpath))
+    return out

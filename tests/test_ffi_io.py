@@ -79,3 +79,42 @@ def test_load_gf_library_on_gpu(tmp_path):
         np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
     with pytest.raises(ValueError):
         ffi.load_gf_library(str(tmp_path), "geodetic_uparr_static_0")
+
+
+def test_discover_project_libraries(tmp_path):
+    rng = np.random.default_rng(2)
+    shape = (2, 6, 2, 4, 8)
+    for comp in ("uparr", "uperp"):
+        for mapn in (0, 1):
+            ffi.save_gf_library(str(tmp_path), rng.standard_normal(shape), np.zeros(2), component=comp, wavename="any_P",
+                                mapnumber=mapn, duration_min=0.5, duration_sampling=0.25, starttime_min=-1.0, starttime_sampling=0.5)
+    ffi.save_gf_library(str(tmp_path), rng.standard_normal(shape), np.zeros(2), component="uparr", wavename="any_S", mapnumber=0)
+    found = ffi.discover_seismic_libraries(str(tmp_path), ("uparr", "uperp"))
+    assert [m for m, _ in found] == ["any_P_0", "any_P_1"]          # any_S_0 lacks uperp
+    wms = ffi.wavemaps_from_directory(str(tmp_path), ("uparr", "uperp"))
+    assert len(wms) == 2 and wms[0]["nt"] == 2 and wms[0]["ns"] == 8 and wms[0]["st_min"] == -1.0
+    assert isinstance(wms[0]["G"]["uperp"], np.memmap)
+    with pytest.raises(ffi.GFLibraryError):
+        ffi.wavemaps_from_directory(str(tmp_path), ("utens",))
+
+
+@pytest.mark.gpu
+def test_engine_from_project_directory(tmp_path):
+    """Libraries written in the reference's on-disk layout, memory-mapped and streamed to HBM, give the same
+    log-likelihoods as the in-memory problem."""
+    from beat_b200 import synthetic
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=4, subfaults=((4, 6, 2.0),), ns=32, ndur=4, seed=17)
+    wm = prob["wavemaps"][0]
+    for comp in prob["slip_vars"]:
+        ffi.save_gf_library(str(tmp_path), wm["G"][comp], np.zeros(wm["nt"]), component=comp, wavename="any_P", mapnumber=0,
+                            duration_min=wm["dur_min"], duration_sampling=wm["dur_step"], starttime_min=wm["st_min"],
+                            starttime_sampling=wm["st_step"])
+    disk = ffi.wavemaps_from_directory(str(tmp_path), prob["slip_vars"])[0]
+    disk.update({k: wm[k] for k in ("data", "U", "slog_pdet", "nsamples", "hyper_idx", "station_idx")})
+    Q = synthetic.draw_chains(prob, 9, seed=3)
+    a = BatchedFFILogLike.from_problem(prob, store_dtype="float32")
+    b = BatchedFFILogLike.from_problem(dict(prob, wavemaps=[disk]), store_dtype="float32")
+    assert np.array_equal(a(Q)[0], b(Q)[0])
+    a.close()
+    b.close()
