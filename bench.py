@@ -299,6 +299,22 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
+    # stdout carries exactly ONE line (the JSON): native libraries (NCCL prints its version banner with printf) write
+    # to file descriptor 1 directly, so fd 1 points at stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = _run_gpu_arm(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -491,10 +507,12 @@ def run_gpu_arm(args):
         }
         if cpu_info is not None:
             line["cpu_baseline"] = cpu_info
-        print(json.dumps(line))
+    else:
+        line = None
     ev.close()
     if n_gpus > 1:
         dist.destroy_process_group()
+    return line
 
 
 def run_c2_llk(args):
