@@ -16,6 +16,7 @@
 #include "stack.cuh"
 #include "aux.cuh"
 #include "gemm.cuh"
+#include "probe.cuh"
 
 using namespace beatgpu;
 
@@ -1246,6 +1247,67 @@ int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms)
     if (!ctx->ev_valid) return fail(ctx, BEATGPU_E_NOTREADY, "last_stack_ms: no fused evaluation yet");
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return BEATGPU_OK;
+}
+
+int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_bytes, int rows_per_warp, int n_launch,
+                         float* ms_per_launch, double* bytes_per_launch)
+{
+    if (!ctx || !ms_per_launch || !bytes_per_launch) return BEATGPU_E_ARG;
+    if (mode < 0 || mode > 2 || row_bytes < 16 || row_bytes > kProbeMaxRow || row_bytes % 16 || ws_bytes < row_bytes ||
+        rows_per_warp < 1 || n_launch < 1)
+        return fail(ctx, BEATGPU_E_ARG, "probe_gather: bad arguments (row_bytes: multiple of 16, <= %d)", kProbeMaxRow);
+    ProbeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.row_bytes = row_bytes;
+    a.row_stride = row_bytes;
+    a.n_rows = 1;
+    while (a.n_rows * 2 * row_bytes <= ws_bytes) a.n_rows *= 2;     // power of two: the row pick is a mask, not a modulo
+    if (a.n_rows > 0x40000000L) return fail(ctx, BEATGPU_E_ARG, "probe_gather: working set too large");
+    a.row_mask = (uint32_t)(a.n_rows - 1);
+    a.rows_per_warp = rows_per_warp;
+    unsigned char* d_ws = nullptr;
+    float* d_sink = nullptr;
+    CK(cudaMalloc((void**)&d_ws, (size_t)a.n_rows * row_bytes));
+    CK(cudaMalloc((void**)&d_sink, 8));
+    CK(cudaMemsetAsync(d_ws, 0, (size_t)a.n_rows * row_bytes, ctx->stream));
+    CK(cudaMemsetAsync(d_sink, 0, 8, ctx->stream));
+    a.ws = d_ws; a.sink = d_sink; a.err = (unsigned int*)(d_sink + 1);
+    // LDG mode: 16 CTAs x 4 warps = all 64 warp slots of every SM.  TMA modes: ring of `depth` rows per warp in
+    // dynamic shared memory, as many CTAs per SM as ~200 KB of rings allow.
+    int per_sm = 16;
+    size_t smem = 0;
+    if (mode != 0) {
+        a.depth = (int)std::max<size_t>(1, std::min<size_t>(kProbeDepth, (size_t)(48 * 1024) / ((size_t)kProbeWarps * row_bytes)));
+        smem = (size_t)kProbeWarps * a.depth * row_bytes + (size_t)kProbeWarps * a.depth * sizeof(uint64_t);
+        per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(200 * 1024) / (smem + 1024)));
+        if (smem > 48 * 1024) {
+            CK(cudaFuncSetAttribute(probe_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute(probe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+    }
+    const int grid = ctx->prop.multiProcessorCount * per_sm;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int i = 0; i < n_launch + 1; ++i) {                   // first launch = warm-up (fills L2)
+        if (i == 1) CK(cudaEventRecord(e0, ctx->stream));
+        if (mode == 0) probe_ldg_kernel<<<grid, kProbeThreads, 0, ctx->stream>>>(a);
+        else if (mode == 1) probe_tma_kernel<true><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
+        else probe_tma_kernel<false><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
+        CKL();
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    unsigned int err = 0;
+    CK(cudaMemcpy(&err, a.err, sizeof(err), cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_ws); cudaFree(d_sink);
+    if (err) return fail(ctx, BEATGPU_E_CUDA, "probe_gather: %u warps timed out waiting for a bulk copy", err);
+    *ms_per_launch = ms / n_launch;
+    *bytes_per_launch = (double)grid * kProbeWarps * (double)rows_per_warp * row_bytes;
     return BEATGPU_OK;
 }
 

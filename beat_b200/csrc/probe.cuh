@@ -1,0 +1,129 @@
+// probe.cuh -- measurement kernels (diagnostics, not on the product path): how fast can this GPU deliver
+//              data-dependent "rows" (a few hundred contiguous bytes each, picked from a working set) to the SMs?
+//
+// gf_stack_chunk_kernel (stack.cuh) gathers one such row per (chain, target, patch, tap) and ncu shows it sitting on
+// the L2->SM return path.  These probes measure that ceiling directly, so bench.py can report the stack kernel
+// against a MEASURED gather peak instead of an assumed 64 B/clk/SM:
+//   mode 0  one warp-wide LDG.128 per row, 8 rows in flight per warp           (the stack kernel's access pattern)
+//   mode 1  one cp.async.bulk (TMA) per row into a per-warp shared-memory ring, lanes then read the row from
+//           shared memory                                                      (what a TMA-staged gather would do)
+//   mode 2  as mode 1 without the shared-memory read                           (pure TMA ingest ceiling)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tma.cuh"
+
+namespace beatgpu {
+
+constexpr int kProbeThreads = 128;
+constexpr int kProbeWarps = kProbeThreads / 32;
+constexpr int kProbeDepth = 8;            // rows (LDG: 512-byte row pieces) in flight per warp
+constexpr int kProbeMaxRow = 16384;       // bytes
+
+struct ProbeArgs {
+    const unsigned char* ws;              // working set, n_rows rows of row_stride bytes
+    long n_rows;                          // power of two
+    uint32_t row_mask;                    // n_rows - 1
+    int row_bytes, row_stride;
+    int rows_per_warp;
+    int depth;                            // TMA modes: ring slots per warp
+    float* sink;
+    unsigned int* err;
+};
+
+__device__ __forceinline__ uint32_t probe_hash(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+// rows <= 512 B: one LDG.128 per lane per row, kProbeDepth rows in flight; longer rows: kProbeDepth 512-byte pieces
+// of the same row in flight.
+__global__ void __launch_bounds__(kProbeThreads) probe_ldg_kernel(ProbeArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * kProbeWarps + (threadIdx.x >> 5);
+    float acc = 0.f;
+    if (a.row_bytes <= 512) {
+        const bool active = lane * 16 < a.row_bytes;
+        for (int it = 0; it < a.rows_per_warp; it += kProbeDepth) {
+            float4 v[kProbeDepth];
+#pragma unroll
+            for (int u = 0; u < kProbeDepth; ++u) {
+                const long r = probe_hash(gw * 7919u + (uint32_t)(it + u)) & a.row_mask;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (active) v[u] = __ldg((const float4*)(a.ws + r * a.row_stride) + lane);
+            }
+#pragma unroll
+            for (int u = 0; u < kProbeDepth; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+        }
+    } else {
+        const int nvec = a.row_bytes / 16;
+        for (int it = 0; it < a.rows_per_warp; ++it) {
+            const long r = probe_hash(gw * 7919u + (uint32_t)it) & a.row_mask;
+            const float4* row = (const float4*)(a.ws + r * a.row_stride);
+            for (int j0 = 0; j0 < nvec; j0 += 32 * kProbeDepth) {
+                float4 v[kProbeDepth];
+#pragma unroll
+                for (int u = 0; u < kProbeDepth; ++u) {
+                    const int j = j0 + u * 32 + lane;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (j < nvec) v[u] = __ldg(row + j);
+                }
+#pragma unroll
+                for (int u = 0; u < kProbeDepth; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
+            }
+        }
+    }
+    if (acc == 123.456f) a.sink[0] = acc;      // never true for the zero-filled working set; defeats dead-code elimination
+}
+
+template <bool READ_SMEM>
+__global__ void __launch_bounds__(kProbeThreads) probe_tma_kernel(ProbeArgs a)
+{
+    extern __shared__ __align__(128) unsigned char probe_smem[];       // [warps][depth][row_bytes] then barriers
+    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5;
+    const int depth = a.depth;
+    unsigned char* ring = probe_smem + (size_t)w * depth * a.row_bytes;
+    uint64_t* bar = (uint64_t*)(probe_smem + (size_t)kProbeWarps * depth * a.row_bytes) + w * depth;
+    const uint32_t gw = blockIdx.x * kProbeWarps + w;
+    if (lane == 0) {
+        for (int s = 0; s < depth; ++s) mbar_init(&bar[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    const int n = a.rows_per_warp;
+    const int nvec = a.row_bytes / 16;
+    if (lane == 0) {
+        for (int s = 0; s < depth && s < n; ++s) {
+            const long r = probe_hash(gw * 7919u + (uint32_t)s) & a.row_mask;
+            mbar_arrive_expect_tx(&bar[s], (uint32_t)a.row_bytes);
+            tma_load_1d(ring + (size_t)s * a.row_bytes, a.ws + r * a.row_stride, (uint32_t)a.row_bytes, &bar[s]);
+        }
+    }
+    float acc = 0.f;
+    for (int it = 0; it < n; ++it) {
+        const int s = it % depth;
+        const uint32_t parity = (uint32_t)(it / depth) & 1u;
+        if (!mbar_wait_bounded(&bar[s], parity)) { if (lane == 0) atomicAdd(a.err, 1u); break; }
+        if (READ_SMEM) {
+            const float4* row = (const float4*)(ring + (size_t)s * a.row_bytes);
+            for (int j = lane; j < nvec; j += 32) {
+                const float4 v = row[j];
+                acc += v.x + v.y + v.z + v.w;
+            }
+        }
+        __syncwarp();                         // all lanes are done with slot s
+        if (lane == 0 && it + depth < n) {
+            const long r = probe_hash(gw * 7919u + (uint32_t)(it + depth)) & a.row_mask;
+            fence_proxy_async();
+            mbar_arrive_expect_tx(&bar[s], (uint32_t)a.row_bytes);
+            tma_load_1d(ring + (size_t)s * a.row_bytes, a.ws + r * a.row_stride, (uint32_t)a.row_bytes, &bar[s]);
+        }
+    }
+    if (acc == 123.456f) a.sink[0] = acc;
+}
+
+}  // namespace beatgpu

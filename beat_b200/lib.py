@@ -92,6 +92,8 @@ _SIGNATURES = {
     "beatgpu_index_violations": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_last_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "beatgpu_probe_gather": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -344,3 +346,10 @@ class Context:
         ms = C.c_float()
         self._check(self._lib.beatgpu_last_stack_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def probe_gather(self, mode, ws_bytes, row_bytes=480, rows_per_warp=4096, n_launch=3):
+        """Diagnostics: measured row-gather bandwidth [GB/s] (mode 0 LDG.128, 1 TMA + smem read, 2 TMA only)."""
+        ms, nbytes = C.c_float(), C.c_double()
+        self._check(self._lib.beatgpu_probe_gather(self._h, mode, int(ws_bytes), row_bytes, rows_per_warp, n_launch,
+                                                   C.byref(ms), C.byref(nbytes)))
+        return nbytes.value / (ms.value * 1e-3) / 1e9

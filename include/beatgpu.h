@@ -225,6 +225,15 @@ int beatgpu_launch_count(beatgpu_ctx* ctx, int64_t* n_launches);
  * with CUDA events: milliseconds of the last loglike batch's stack kernel(s).                */
 int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms);
 
+/* Diagnostics (not on the product path): measured ceiling of the access pattern the GF stacking uses.  Gathers
+ * pseudo-random rows of row_bytes (multiple of 16, <= 16384) from a zero-filled working set of ws_bytes with
+ * mode 0 = one warp-wide 16-byte-per-lane load per row (gf_stack_chunk_kernel's pattern), mode 1 = one bulk
+ * asynchronous copy (TMA) per row into shared memory which the warp then reads, mode 2 = the bulk copies alone.
+ * A working set well below the 126 MB L2 measures the L2->SM path, one far above it the HBM gather rate.
+ * bench.py reports the stack kernel against this number.                                                    */
+int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_bytes, int rows_per_warp,
+                         int n_launch, float* ms_per_launch, double* bytes_per_launch);
+
 #ifdef __cplusplus
 }
 #endif
