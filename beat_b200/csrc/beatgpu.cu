@@ -17,6 +17,7 @@
 #include "aux.cuh"
 #include "gemm.cuh"
 #include "probe.cuh"
+#include "geom.cuh"
 
 using namespace beatgpu;
 
@@ -45,6 +46,27 @@ struct WaveMap {
     double* d_slog_pdet = nullptr;
     int misfit_mode = -1, bw = 0, dense_upper = 1;
     int out_ofs = 0;
+    int geom = -1;                  // >= 0: geometry-mode wavemap (index into ctx->gwmaps); no GF library of its own
+};
+
+// geometry mode (BASELINE config 2): a pyrocko-style GF store and the per-wavemap static operands
+struct GeomStore {
+    GeomStoreDev dev;
+    float* d_traces = nullptr;
+    int* d_itmin = nullptr;
+    int* d_nsamp = nullptr;
+    int max_nsamp = 0;
+};
+
+struct GeomWaveMap {
+    int store_id = 0, nt = 0, nr = 0, nraw_max = 0, n4 = 0;
+    double *d_rcv_lat = nullptr, *d_rcv_lon = nullptr;
+    int *d_rcv_itmin = nullptr, *d_rcv_nraw = nullptr, *d_rcv_first = nullptr, *d_tgt_of = nullptr;
+    float* d_tgt_f = nullptr;
+    int *d_tgt_nraw = nullptr, *d_tgt_ibeg = nullptr;
+    double* d_taper = nullptr;      // nullptr: all factors are 1 (chop between b and c)
+    int nsec = 1, ord = 1, demean = 0;
+    double fb[kGeomMaxSec][kGeomMaxOrder + 1], fa[kGeomMaxSec][kGeomMaxOrder + 1];
 };
 
 struct Geodetic {
@@ -115,6 +137,16 @@ struct beatgpu_ctx {
     size_t partial_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool ev_valid = false;
+    // geometry mode
+    std::vector<GeomStore> gstores;
+    std::vector<GeomWaveMap> gwmaps;
+    bool glayout_set = false;
+    beatgpu_geom_layout glayout;
+    double* d_gfixed = nullptr;
+    double ev_lat = 0, ev_lon = 0, stf_anchor = -1.0;
+    void *d_rplan = nullptr, *d_cplan = nullptr, *d_rawT = nullptr, *d_gmean = nullptr;
+    size_t g_rplan_bytes = 0, g_cplan_bytes = 0, g_raw_bytes = 0, g_mean_bytes = 0;
+    unsigned int* d_gerr = nullptr;
 };
 
 namespace {
@@ -192,7 +224,7 @@ void assign_out_offsets(beatgpu_ctx* ctx)
 int ensure_scratch(beatgpu_ctx* ctx, int B)
 {
     const int n_out = std::max(1, n_outputs(ctx));
-    const int n_par = ctx->layout_set ? ctx->layout.n_params : 1;
+    const int n_par = std::max(ctx->layout_set ? ctx->layout.n_params : 1, ctx->glayout_set ? ctx->glayout.n_params : 1);
     if (B <= ctx->cap_B && n_out <= ctx->cap_n_out && n_par <= ctx->cap_n_params) return BEATGPU_OK;
     const int nb = std::max(B, ctx->cap_B);
     cudaFree(ctx->d_q); cudaFree(ctx->d_logpts); cudaFree(ctx->d_like); cudaFree(ctx->d_t0); cudaFree(ctx->d_bad);
@@ -483,6 +515,13 @@ void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
     cudaFree(ctx->d_viol);
     cudaFree(ctx->d_partial);
     for (int i = 0; i < 6; ++i) cudaFree(ctx->d_tmp[i]);
+    for (auto& st : ctx->gstores) { cudaFree(st.d_traces); cudaFree(st.d_itmin); cudaFree(st.d_nsamp); }
+    for (auto& g : ctx->gwmaps) {
+        cudaFree(g.d_rcv_lat); cudaFree(g.d_rcv_lon); cudaFree(g.d_rcv_itmin); cudaFree(g.d_rcv_nraw); cudaFree(g.d_rcv_first);
+        cudaFree(g.d_tgt_of); cudaFree(g.d_tgt_f); cudaFree(g.d_tgt_nraw); cudaFree(g.d_tgt_ibeg); cudaFree(g.d_taper);
+    }
+    cudaFree(ctx->d_gfixed); cudaFree(ctx->d_rplan); cudaFree(ctx->d_cplan); cudaFree(ctx->d_rawT); cudaFree(ctx->d_gmean);
+    cudaFree(ctx->d_gerr);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -618,6 +657,7 @@ int beatgpu_add_wavemap(beatgpu_ctx* ctx, int nt, int ns, int interp, const int3
     if (nt <= 0 || ns <= 0 || !hyper_idx || !nsamples || !wmap_id) return fail(ctx, BEATGPU_E_ARG, "add_wavemap: bad arguments");
     if (interp != BEATGPU_NEAREST && interp != BEATGPU_MULTILINEAR)
         return fail(ctx, BEATGPU_E_ARG, "add_wavemap: interpolation scheme %d not implemented", interp);
+    if (!ctx->gwmaps.empty()) return fail(ctx, BEATGPU_E_ARG, "add_wavemap: the context holds geometry-mode wavemaps; use one context per mode");
     CK(cudaSetDevice(ctx->device));
     WaveMap w;
     w.nt = nt; w.ns = ns; w.interp = interp;
@@ -936,9 +976,13 @@ int beatgpu_stack_batch(beatgpu_ctx* ctx, int wmap_id, int B, int nvar, const do
     return check_violations(ctx, "stack_batch");
 }
 
-static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* d_resid, const double* d_hyp, int n_hypers, double* d_logpts)
+// d_hyp + c*hyp_stride + hyper_idx[t] is the hyperparameter of (chain c, target t); logpts[c*logpts_sc + out_ofs + t]
+static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* d_resid, const double* d_hyp, long hyp_stride,
+                             double* d_logpts, long logpts_sc = -1, int out_ofs = 0, const unsigned char* chain_bad = nullptr)
 {
     int rc;
+    const long n_hypers = hyp_stride;
+    if (logpts_sc < 0) logpts_sc = w.nt;
     if (w.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && B >= 32) {
         // dense weights: Z_t = U_t R_t for all chains on the FP64 tensor cores, straight from the caller's layout
         const int mt = (w.ns + kGemmTile - 1) / kGemmTile;
@@ -957,8 +1001,8 @@ static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* 
         memset(&f, 0, sizeof(f));
         f.B = B; f.nt = w.nt; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];
         f.slog_pdet = w.d_slog_pdet; f.nsamp = w.d_nsamp; f.hyper_idx = w.d_hyper_idx;
-        f.hyp = d_hyp; f.hyp_sc = n_hypers; f.chain_bad = nullptr;
-        f.logpts = d_logpts; f.logpts_sc = w.nt; f.out_ofs = 0;
+        f.hyp = d_hyp; f.hyp_sc = n_hypers; f.chain_bad = chain_bad;
+        f.logpts = d_logpts; f.logpts_sc = logpts_sc; f.out_ofs = out_ofs;
         seismic_finish_kernel<<<(unsigned)(((long)B * w.nt + 127) / 128), 128, 0, ctx->stream>>>(f);
         CKL();
     } else {
@@ -969,7 +1013,7 @@ static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* 
         a.hyp = d_hyp; a.hyp_sc = n_hypers; a.hyper_idx = w.d_hyper_idx;
         a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
         a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
-        a.logpts = d_logpts; a.logpts_sc = w.nt; a.out_ofs = 0;
+        a.logpts = d_logpts; a.logpts_sc = logpts_sc; a.out_ofs = out_ofs; a.chain_bad = chain_bad;
         const size_t smem = (size_t)w.ns * sizeof(double);
         if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
@@ -1057,6 +1101,7 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
     const beatgpu_layout& L = ctx->layout;
     const int n_out = n_outputs(ctx);
     for (auto& w : ctx->wmaps) {
+        if (w.geom >= 0) return fail(ctx, BEATGPU_E_ARG, "ffi_loglike_batch: the context holds geometry-mode wavemaps; use beatgpu_geom_loglike_batch");
         if ((rc = check_lib(ctx, w, L.n_slipvars))) return rc;
         if (!w.d_data) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: data of a wavemap not uploaded");
         if (w.misfit_mode < 0) return fail(ctx, BEATGPU_E_NOTREADY, "ffi_loglike_batch: weights of a wavemap not uploaded");
@@ -1312,3 +1357,5 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
 }
 
 }  // extern "C"
+
+#include "geom_host.inc"

@@ -56,6 +56,16 @@ class Layout(C.Structure):
     ]
 
 
+class GeomLayout(C.Structure):
+    """beatgpu_geom_layout (geometry-mode parameter vector -> DC source variables)."""
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_params", "off_east_shift", "off_north_shift", "off_depth", "off_strike", "off_dip", "off_rake",
+        "off_magnitude", "off_time", "off_duration", "off_hypers", "n_hypers")]
+
+
+GEOM_VARS = ("east_shift", "north_shift", "depth", "strike", "dip", "rake", "magnitude", "time", "duration")
+GEOM_MAX_ORDER = 8
+
 # every symbol include/beatgpu.h declares, with its ctypes signature (tests check the .so exports them all)
 _P = C.c_void_p
 _SIGNATURES = {
@@ -92,6 +102,14 @@ _SIGNATURES = {
     "beatgpu_index_violations": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_last_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "beatgpu_geom_set_source": (C.c_int, [_P, C.POINTER(GeomLayout), _P, C.c_double, C.c_double, C.c_double]),
+    "beatgpu_geom_upload_store": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P,
+                                            C.POINTER(C.c_int)]),
+    "beatgpu_geom_add_wavemap": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
+                                           C.c_int, _P, _P, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]),
+    "beatgpu_geom_loglike_batch": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "beatgpu_geom_loglike_batch_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
+    "beatgpu_geom_synthetics_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "beatgpu_probe_gather": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double)]),
 }
@@ -353,3 +371,74 @@ class Context:
         self._check(self._lib.beatgpu_probe_gather(self._h, mode, int(ws_bytes), row_bytes, rows_per_warp, n_launch,
                                                    C.byref(ms), C.byref(nbytes)))
         return nbytes.value / (ms.value * 1e-3) / 1e9
+
+    # ------------------------------------------------------------------ geometry mode (config 2)
+    def geom_set_source(self, layout, fixed, event_lat, event_lon, stf_anchor=-1.0):
+        fx = None if fixed is None else _f64(fixed)
+        self._check(self._lib.beatgpu_geom_set_source(self._h, C.byref(layout), _ptr(fx), float(event_lat), float(event_lon),
+                                                      float(stf_anchor)))
+        self._geom_n_params = layout.n_params
+
+    def geom_upload_store(self, traces, itmin, nsamples, z0, dz, x0, dx, deltat):
+        traces = np.ascontiguousarray(traces, dtype=np.float32)
+        if traces.ndim != 4:
+            raise ValueError("GF store traces must be (n_depths, n_distances, n_components, n_samples)")
+        itmin = np.ascontiguousarray(itmin, dtype=np.int32)
+        nsamples = np.ascontiguousarray(nsamples, dtype=np.int32)
+        if itmin.shape != traces.shape[:3] or nsamples.shape != traces.shape[:3]:
+            raise ValueError("itmin / nsamples must have one entry per record")
+        dims = np.asarray(traces.shape, dtype=np.int64)
+        sid = C.c_int()
+        self._check(self._lib.beatgpu_geom_upload_store(self._h, _ptr(dims), z0, dz, x0, dx, deltat, _ptr(traces), _ptr(itmin),
+                                                        _ptr(nsamples), C.byref(sid)))
+        return sid.value
+
+    def geom_add_wavemap(self, store_id, ns, interpolation, lats, lons, azimuths, dips, arrival_times, taper_abcd,
+                         chop_bounds, sections, hyper_idx, nsamples):
+        """sections: [(b, a, demean), ...] as scipy.signal.butter returns them (demean only on the first)."""
+        lats, lons, az, dp, at = (_f64(x) for x in (lats, lons, azimuths, dips, arrival_times))
+        nt = lats.size
+        abcd = _f64(taper_abcd, (4,))
+        lo, hi = ("abcd".index(c) for c in chop_bounds)
+        nsec = len(sections)
+        order = np.zeros(max(nsec, 1), dtype=np.int32)
+        sb = np.zeros((max(nsec, 1), GEOM_MAX_ORDER + 1))
+        sa = np.zeros((max(nsec, 1), GEOM_MAX_ORDER + 1))
+        for i, (b, a, demean) in enumerate(sections):
+            b, a = np.atleast_1d(b), np.atleast_1d(a)
+            if demean and i > 0:
+                raise NotImplementedError("demeaning is supported before the first filter section only")
+            if max(b.size, a.size) - 1 > GEOM_MAX_ORDER:
+                raise NotImplementedError("IIR sections up to order %d" % GEOM_MAX_ORDER)
+            order[i] = max(b.size, a.size) - 1
+            sb[i, :b.size] = b
+            sa[i, :a.size] = a
+        demean_first = int(bool(nsec and sections[0][2]))
+        hidx, nsm = _i32(hyper_idx), _i32(nsamples)
+        wid = C.c_int()
+        self._check(self._lib.beatgpu_geom_add_wavemap(
+            self._h, store_id, nt, ns, INTERPOLATION[interpolation], _ptr(lats), _ptr(lons), _ptr(az), _ptr(dp), _ptr(at),
+            _ptr(abcd), lo, hi, nsec, _ptr(order), _ptr(sb), _ptr(sa), demean_first, _ptr(hidx), _ptr(nsm), C.byref(wid)))
+        return wid.value
+
+    def geom_loglike_batch(self, Q):
+        Q = _f64(Q)
+        B = Q.shape[0]
+        n_out = self.n_outputs()
+        logpts, like = np.empty((B, n_out)), np.empty(B)
+        self._check(self._lib.beatgpu_geom_loglike_batch(self._h, B, _ptr(Q), _ptr(logpts), _ptr(like)))
+        return logpts, like
+
+    def geom_loglike_batch_ptr(self, B, q_ptr, logpts_ptr, like_ptr):
+        self._check(self._lib.beatgpu_geom_loglike_batch(self._h, int(B), C.c_void_p(q_ptr), C.c_void_p(logpts_ptr),
+                                                         C.c_void_p(like_ptr)))
+
+    def geom_loglike_batch_dev(self, B, q_ptr, logpts_ptr, like_ptr):
+        self._check(self._lib.beatgpu_geom_loglike_batch_dev(self._h, int(B), C.c_void_p(q_ptr), C.c_void_p(logpts_ptr),
+                                                             C.c_void_p(like_ptr or 0)))
+
+    def geom_synthetics_batch(self, wmap, Q, nt, ns):
+        Q = _f64(Q)
+        out = np.empty((Q.shape[0], nt, ns))
+        self._check(self._lib.beatgpu_geom_synthetics_batch(self._h, wmap, Q.shape[0], _ptr(Q), _ptr(out)))
+        return out

@@ -203,3 +203,114 @@ def config_c3(small=False, **kw):
         args = dict(nt=64, subfaults=((10, 20, 2.0),), ns=120, ndur=17, nst=64)
     args.update(kw)
     return make_problem(**args)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# geometry mode (BASELINE config 2): double-couple point source, GF store, stations x components
+# ----------------------------------------------------------------------------------------------------------
+GEOM_VARS = ("east_shift", "north_shift", "depth", "strike", "dip", "rake", "magnitude", "time", "duration")
+
+
+def _station_latlon(lat0, lon0, azimuth_deg, distance_m):
+    """Destination point on a sphere (placement of synthetic stations only; not part of any parity claim)."""
+    d, az = distance_m / 6371000.0, np.deg2rad(azimuth_deg)
+    la0, lo0 = np.deg2rad(lat0), np.deg2rad(lon0)
+    la = np.arcsin(np.sin(la0) * np.cos(d) + np.cos(la0) * np.sin(d) * np.cos(az))
+    lo = lo0 + np.arctan2(np.sin(az) * np.sin(d) * np.cos(la0), np.cos(d) - np.sin(la0) * np.sin(la))
+    return np.rad2deg(la), np.rad2deg(lo)
+
+
+def make_gf_store(nz, nx, z0, dz, x0, dx, deltat, nrec, seed=77, vp=6.0e3, vs=3.5e3, lead=10.0, ragged=True):
+    """Synthetic GF store in the layout of a pyrocko type-A store with 10 components: per (source depth, distance)
+    node and component a float32 record with its own first-sample index and length.  Records hold a P and an S
+    wavelet with move-out plus a small permanent offset after S (so that the repeated end value matters)."""
+    rng = np.random.default_rng(seed)
+    z = z0 + dz * np.arange(nz)[:, None]
+    x = x0 + dx * np.arange(nx)[None, :]
+    R = np.sqrt(z ** 2 + x ** 2)
+    tp, ts = R / vp, R / vs
+    itmin = np.floor((tp - lead) / deltat).astype(np.int32)[:, :, None] + rng.integers(-3, 4, (nz, nx, 10)).astype(np.int32)
+    nsamples = np.full((nz, nx, 10), nrec, dtype=np.int32)
+    if ragged:
+        nsamples -= rng.integers(0, max(1, nrec // 8), (nz, nx, 10)).astype(np.int32)
+        short = rng.random((nz, nx, 10)) < 0.1
+        nsamples[short] = np.maximum(8, nrec // 3)
+    t = (itmin[..., None] + np.arange(nrec)[None, None, None, :]) * deltat
+    ap = rng.standard_normal((1, 1, 10, 1)) * 1e-19 * (1.0e5 / R)[:, :, None, None]
+    as_ = rng.standard_normal((1, 1, 10, 1)) * 2e-19 * (1.0e5 / R)[:, :, None, None]
+    sp, ss = 1.5 + 0.2 * rng.random((1, 1, 10, 1)), 2.5 + 0.3 * rng.random((1, 1, 10, 1))
+    xp_, xs_ = (t - tp[:, :, None, None]) / sp, (t - ts[:, :, None, None]) / ss
+    traces = ap * ricker(xp_) + as_ * (ricker(xs_) + 0.15 / (1.0 + np.exp(-np.clip(xs_, -40, 40))))
+    traces = traces.astype(np.float32)
+    traces[np.arange(nrec)[None, None, None, :] >= nsamples[..., None]] = 0.0
+    return dict(deltat=deltat, nz=nz, nx=nx, z0=z0, dz=dz, x0=x0, dx=dx, traces=traces, itmin=itmin, nsamples=nsamples,
+                vp=vp, vs=vs)
+
+
+def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=0.5, taper=(-7.5, -5.0, 15.0, 17.5),
+                          interpolation="multilinear", filterer=None, dist_range=(500e3, 700e3), shift_km=10.0,
+                          depth_range_km=(2.0, 10.0), dz=2.0e3, dx=4.0e3, nrec=200, time_bounds=(-3.0, 3.0),
+                          duration_bounds=(0.0, 6.0), seed=99, hp_specific=False, ragged=True, lead=10.0):
+    """Synthetic geometry-mode seismic problem (one wavemap, one DC source).  ``data`` / weights are attached later by
+    ``attach_geometry_data`` from synthetics of a reference point (tests: the oracle's; bench: the GPU engine's)."""
+    rng = np.random.default_rng(seed)
+    if filterer is None:
+        filterer = [dict(kind="stepwise", order=4, lower_corner=0.01, upper_corner=0.4)]   # heart.Filter defaults, corners for 2 Hz
+    a, b, c, d = taper
+    if int(np.ceil((c - b) / deltat)) != ns:
+        raise ValueError("taper b..c is %g s = %g samples, ns = %d" % (c - b, (c - b) / deltat, ns))
+    ev_lat, ev_lon = 37.5, 15.0
+    margin = shift_km * 1e3 * 1.5 + 2 * dx
+    x0 = np.floor((dist_range[0] - margin) / dx) * dx
+    nx = int(np.ceil((dist_range[1] + margin - x0) / dx)) + 1
+    z0 = depth_range_km[0] * 1e3 - dz
+    nz = int(np.ceil((depth_range_km[1] * 1e3 + dz - z0) / dz)) + 1
+    store = make_gf_store(nz, nx, z0, dz, x0, dx, deltat, nrec, seed=seed + 1, ragged=ragged, lead=lead)
+    chan = dict(N=(0.0, 0.0), E=(90.0, 0.0), Z=(0.0, -90.0))
+    st_az = rng.uniform(0.0, 360.0, n_stations)
+    st_dist = rng.uniform(dist_range[0], dist_range[1], n_stations)
+    lats, lons, azis, dips, arr, codes = [], [], [], [], [], []
+    depth_ref = 0.5 * (depth_range_km[0] + depth_range_km[1]) * 1e3
+    for s in range(n_stations):
+        la, lo = _station_latlon(ev_lat, ev_lon, st_az[s], st_dist[s])
+        # fixed phase arrival of the reference event, snapped to the sampling grid (heart.get_phase_arrival_time, snap=True)
+        at = np.rint(np.sqrt(st_dist[s] ** 2 + depth_ref ** 2) / store["vp"] / deltat) * deltat
+        for ch in channels:
+            lats.append(la); lons.append(lo); azis.append(chan[ch][0]); dips.append(chan[ch][1]); arr.append(at)
+            codes.append("ST%02d.%s" % (s, ch))
+    nt = len(lats)
+    n_hypers = nt if hp_specific else 1
+    var_order = [(v, 1) for v in GEOM_VARS] + [("hypers", n_hypers)]
+    offsets, o = {}, 0
+    for name, size in var_order:
+        offsets[name] = o
+        o += size
+    priors = dict(east_shift=(-shift_km, shift_km), north_shift=(-shift_km, shift_km), depth=depth_range_km,
+                  strike=(0.0, 360.0), dip=(0.0, 90.0), rake=(-180.0, 180.0), magnitude=(5.5, 6.5), time=time_bounds,
+                  duration=duration_bounds, hypers=(np.zeros(n_hypers), np.full(n_hypers, 4.0)))
+    priors = {k: (np.atleast_1d(np.asarray(v[0], dtype=float)), np.atleast_1d(np.asarray(v[1], dtype=float))) for k, v in priors.items()}
+    wm = dict(nt=nt, ns=ns, deltat=deltat, interpolation=interpolation, lats=np.array(lats), lons=np.array(lons),
+              azimuths=np.array(azis), dips=np.array(dips), arrival_times=np.array(arr), taper=tuple(taper),
+              filterer=filterer, codes=codes, nsamples=np.full(nt, ns, dtype=np.int32),
+              hyper_idx=(np.arange(nt, dtype=np.int32) if hp_specific else np.zeros(nt, dtype=np.int32)),
+              data=None, U=None, slog_pdet=None)
+    return dict(mode="geometry", store=store, event=dict(lat=ev_lat, lon=ev_lon), stf_anchor=-1.0, var_order=var_order,
+                offsets=offsets, n_params=o, n_hypers=n_hypers, priors=priors, wavemaps=[wm], seed=seed)
+
+
+def attach_geometry_data(gprob, synths, noise="exponential", seed=5, rel_sigma=0.05, iw=0):
+    """data = synthetics of a reference point + coloured noise; weights U / log-dets from the noise covariance
+    (Covariance.chol_inverse / log_pdet)."""
+    rng = np.random.default_rng(seed)
+    wm = gprob["wavemaps"][iw]
+    nt, ns = wm["nt"], wm["ns"]
+    synths = np.asarray(synths, dtype=np.float64).reshape(nt, ns)
+    sigma = rel_sigma * max(np.abs(synths).max(), 1e-30)
+    Ct = _noise_cov(noise, ns, wm["deltat"], sigma, rng)
+    cov = Covariance(data=Ct)
+    Lc = np.linalg.cholesky(Ct)
+    wm["data"] = synths + (Lc.dot(rng.standard_normal((ns, nt)))).T
+    wm["U"] = np.broadcast_to(cov.chol_inverse, (nt, ns, ns))
+    wm["slog_pdet"] = np.full(nt, cov.log_pdet)
+    wm["noise"] = noise
+    return gprob

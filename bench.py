@@ -462,11 +462,8 @@ def _run_gpu_arm(args):
     sampler_value = n_gpus * B * args.steps / (float(t.item()) / 1e3)
 
     if rank == 0:
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        _pk = load_peaks()
+        peak, peak_src = _pk["hbm_gbs"], _pk["source"]
         bytes_launch = algorithmic_bytes_per_eval(a, args.store, args.interpolation) * B
         k_ms = float(np.mean(stack_ms))
         achieved = bytes_launch / (k_ms / 1e3) / 1e9
@@ -557,6 +554,117 @@ def run_c2_llk(args):
     ctx.close()
 
 
+def c2_problem(quick=False):
+    """BASELINE config 2: DC point source, 32 stations x 3 components x 2048 samples (2 Hz, b..c = 1024 s), stepwise
+    Butterworth filter, Toeplitz (exponential) covariance.  Synthetic type-A GF store (10 components), ~0.6 GB > L2."""
+    from beat_b200 import synthetic
+    if quick:
+        return synthetic.make_geometry_problem(n_stations=4, seed=7)
+    return synthetic.make_geometry_problem(
+        n_stations=32, ns=2048, taper=(-34.0, -24.0, 1000.0, 1010.0), nrec=2300, lead=60.0, dist_range=(2000e3, 4000e3),
+        dx=4e3, dz=2.5e3, depth_range_km=(5.0, 30.0), duration_bounds=(0.0, 10.0), seed=7,
+        filterer=[dict(kind="stepwise", order=4, lower_corner=0.005, upper_corner=0.2)])
+
+
+def load_peaks():
+    """Roofline denominator: the driver-written measured HBM copy bandwidth, else the profiling recipe's fallback."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return {"hbm_gbs": json.load(open(peaks_path))["hbm_gbs"], "source": "measured (MEASURED_PEAKS.json hbm_gbs)"}
+    return {"hbm_gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+_C2 = {}
+
+
+def _c2_cpu_eval(i):
+    from oracle import geom_oracle
+    from beat_b200 import synthetic
+    g = _C2["gprob"]
+    return geom_oracle.geometry_seismic_eval(g, synthetic.split_point(g, _C2["Q"][i % len(_C2["Q"])])).sum()
+
+
+def run_c2(args):
+    """For the record (not the BASELINE metric): the geometry-mode seismic forward model + llk of config 2 end to end
+    on one GPU -- plan, TMA-staged delay-and-sum over the GF store, IIR filter + taper + chop + banded misfit."""
+    import torch
+    from beat_b200 import synthetic
+    from beat_b200.geometry import BatchedGeometryLogLike
+    dev = torch.device("cuda", 0)
+    B = args.chains if args.chains != 4000 else 2000
+    log("building the config-2 problem")
+    gprob = c2_problem(args.quick)
+    wm = gprob["wavemaps"][0]
+    ev = BatchedGeometryLogLike.from_problem(gprob, device=0, upload_data=False)
+    q_true = synthetic.draw_chains(gprob, 1, seed=1)
+    synthetic.attach_geometry_data(gprob, ev.get_synthetics(q_true[0]))
+    # banded weights straight from the Toeplitz covariance: the dense [nt, ns, ns] array is only materialised per target
+    ev.upload_data(0, wm["data"], wm["U"], wm["slog_pdet"])
+    Qs = [synthetic.draw_chains(gprob, B, seed=100 + i) for i in range(4)]
+    q_dev = [torch.from_numpy(q).to(dev) for q in Qs]
+    lp = torch.empty((B, ev.n_out), dtype=torch.float64, device=dev)
+    lk = torch.empty((B,), dtype=torch.float64, device=dev)
+    for i in range(args.warmup):
+        ev.eval_device(q_dev[i % 4], lp, lk)
+    torch.cuda.synchronize()
+    viol = ev.ctx.index_violations()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sum_ms = []
+    launches0 = ev.ctx.launch_count()
+    e0.record()
+    for i in range(args.steps):
+        ev.eval_device(q_dev[i % 4], lp, lk)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = ev.ctx.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    for i in range(args.steps):                                # kernel time of the delay-and-sum, one step at a time
+        ev.eval_device(q_dev[i % 4], lp, lk)
+        torch.cuda.synchronize()
+        sum_ms.append(ev.ctx.last_stack_ms())
+    k_ms = float(np.mean(sum_ms))
+    finite = bool(torch.isfinite(lk).all().item())
+    # e2e: pinned host q -> H2D -> kernels -> D2H(logpts, like)
+    q_pin = [torch.from_numpy(q).pin_memory() for q in Qs]
+    lp_pin = torch.empty((B, ev.n_out), dtype=torch.float64).pin_memory()
+    lk_pin = torch.empty((B,), dtype=torch.float64).pin_memory()
+    ev.ctx.set_stream(0, external=False)
+    for i in range(args.warmup):
+        ev.eval_pinned(B, q_pin[i % 4].data_ptr(), lp_pin.data_ptr(), lk_pin.data_ptr())
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ev.eval_pinned(B, q_pin[i % 4].data_ptr(), lp_pin.data_ptr(), lk_pin.data_ptr())
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    peaks = load_peaks()
+    alg = ev._bytes_per_eval * B
+    line = {"metric": "forward+loglike evals/sec (C2 geometry-mode DC point source; not the BASELINE metric)",
+            "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "dtype": "f64 (GF sum in f32 like the store)", "data": "synthetic",
+            "config": {"workload": "C2 seismic DC point source: %d stations x 3 components x %d samples, %s, stepwise Butterworth "
+                                   "order 4, exponential covariance" % (wm["nt"] // 3, wm["ns"], wm["interpolation"]),
+                       "chains_per_gpu": B, "gf_store_MB": gprob["store"]["traces"].nbytes / 1e6,
+                       "l2": "q rotates between steps; raw-trace scratch %.1f GB > L2" % (B * wm["nt"] * 2200 * 4 / 1e9)},
+            "e2e": {"value": B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(Qs[0].nbytes), "d2h_bytes_per_step": int(lp_pin.numel() * 8 + lk_pin.numel() * 8)},
+            "gpu_launches": int(launches), "all_finite": finite, "index_violations_warmup": int(viol),
+            "roofline": {"bound": "hbm", "kernel": "geom_plan_kernel+gf_delay_sum_kernel", "achieved": alg / (k_ms / 1e3) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
+                         "kernel_share_of_step": k_ms / ms,
+                         "note": "rows of one receiver are shared by all chains and by its 3 channels, so they are served from L2"}}
+    if not args.no_cpu_baseline:
+        n = 4 if not args.quick else 8
+        cores = min(usable_cores(), n)
+        _C2["gprob"], _C2["Q"] = gprob, Qs[0][:n]
+        t0 = time.perf_counter()
+        _c2_cpu_eval(0)
+        one = time.perf_counter() - t0
+        dt = pool_map(_c2_cpu_eval, list(range(n)), cores, timeout=600)
+        line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port", "value_1core": 1.0 / one,
+                                "sample": "%d chains, oracle restatement (numpy delay-and-sum + scipy lfilter + numpy llk), fork pool" % n}
+    ev.close()
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -570,13 +678,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="exponential", choices=["exponential", "variance", "dense"],
                     help="data covariance structure (exponential = BASELINE config; dense = full non-Toeplitz, for the record)")
-    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5", "c2llk"], help="c3 = BASELINE.json metric; c4/c5 for the record")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5", "c2llk", "c2"], help="c3 = BASELINE.json metric; c4/c5 for the record")
     args = ap.parse_args()
     global CONFIG, NOISE
     CONFIG, NOISE = args.config, args.noise
     args.warmup = max(args.warmup, 3)
     if args.config == "c2llk":
         run_c2_llk(args)
+    elif args.config == "c2":
+        run_c2(args)
     elif args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -225,6 +225,67 @@ int beatgpu_launch_count(beatgpu_ctx* ctx, int64_t* n_launches);
  * with CUDA events: milliseconds of the last loglike batch's stack kernel(s).                */
 int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms);
 
+/* ---------------------------------------------------------------- geometry mode -------------
+ * The point-source ("geometry") seismic composite of BASELINE config 2: per chain a double-couple source
+ * (east_shift, north_shift, depth [km], strike, dip, rake [deg], magnitude, time [s], STF duration [s]) is turned into
+ * synthetic seismograms by a weighted, delayed sum of GF-store traces, filtered, tapered, chopped and compared with
+ * the data.  Replaces SeisSynthesizer.perform (beat/pytensorf.py:241-302) -> heart.seis_synthetics
+ * (beat/heart.py:3564-3762) -> post_process_trace (:3466-3525) and the likelihood of
+ * SeismicGeometryComposite.get_formula (beat/models/seismic.py:737-837).  The synthesis itself is pyrocko's
+ * (un-vendored dependency, >= 2023.10.11): its published algorithm is restated, see csrc/geom.cuh and
+ * oracle/geom_oracle.py.  Times are relative to the reference event's origin time.  Supported: one DC source per
+ * wavemap, HalfSinusoid STF, GF component scheme 'elastic10', store type A (source depth x distance), pre_stack_cut
+ * = True (the reference's default), time domain, no station corrections.  A context is either finite-fault or
+ * geometry mode.                                                                                            */
+
+/* Flat parameter vector -> source variables (pymc bijection over value_vars, beat/backend.py:147,163-165; variable
+ * list beat/config.py:83-94 for DCSource + 'duration' of the STF, beat/utility.py:773-797).  Offset -1 = not
+ * sampled: value taken from fixed[] in the canonical order [east_shift, north_shift, depth, strike, dip, rake,
+ * magnitude, time, duration, hypers...].                                                                    */
+typedef struct beatgpu_geom_layout {
+    int32_t n_params;
+    int32_t off_east_shift, off_north_shift, off_depth;      /* [km] (utility.adjust_point_units converts to m) */
+    int32_t off_strike, off_dip, off_rake;                   /* [deg]                                            */
+    int32_t off_magnitude, off_time, off_duration;
+    int32_t off_hypers, n_hypers;
+} beatgpu_geom_layout;
+/* event_lat/lon: origin the source's north/east shifts refer to (the reference event, beat/config.py:2045-2066);
+ * stf_anchor: HalfSinusoidSTF.anchor, -1 in the reference (beat/config.py:2060).                             */
+int beatgpu_geom_set_source(beatgpu_ctx* ctx, const beatgpu_geom_layout* layout, const double* fixed,
+                            double event_lat, double event_lon, double stf_anchor);
+
+/* Upload a GF store (what engine.get_store(target.store_id) opens in the reference, beat/heart.py:3657): dims =
+ * (n_source_depths, n_distances, 10, row_length); record (iz, ix, g) holds nsamples[iz,ix,g] <= row_length float32
+ * samples starting at sample index itmin[iz,ix,g] (time = index * deltat after the source origin); outside its span
+ * a record repeats its first / last sample.  z0/dz, x0/dx: source-depth and distance axes [m].               */
+int beatgpu_geom_upload_store(beatgpu_ctx* ctx, const int64_t dims[4], double z0, double dz, double x0, double dx,
+                              double deltat, const float* traces, const int32_t* itmin, const int32_t* nsamples,
+                              int* store_id);
+
+/* Declare a geometry-mode wavemap of n_targets datasets with n_samples each (the constructor arguments of
+ * SeisSynthesizer, beat/pytensorf.py:160-206): target positions [deg] and sensor orientation (azimuth, dip [deg]:
+ * N = (0, 0), E = (90, 0), Z = (0, -90)), the fixed phase arrival times [s] (wmap._arrival_times), the ArrivalTaper
+ * (a, b, c, d) [s] relative to the arrival (beat/heart.py:266-336), chop bounds as indices into (a, b, c, d)
+ * (the likelihood uses 1, 2 = ["b", "c"], seismic.py:755), and the filter as a cascade of IIR sections exactly as
+ * scipy.signal.butter returns them (Filter.apply, heart.py:377-392: stepwise = high-pass with demean, then
+ * low-pass): sec_b / sec_a are [n_sections, 9] (zero padded), demean_first != 0 removes the trace mean before the
+ * first section.  Targets sharing position and window are synthesised together.  Data and weights are uploaded
+ * with beatgpu_upload_data / beatgpu_update_weights under the returned id.                                   */
+int beatgpu_geom_add_wavemap(beatgpu_ctx* ctx, int store_id, int n_targets, int n_samples, int interpolation,
+                             const double* lats, const double* lons, const double* azimuths, const double* dips,
+                             const double* arrival_times, const double taper_abcd[4], int chop_lo, int chop_hi,
+                             int n_sections, const int32_t* sec_order, const double* sec_b, const double* sec_a,
+                             int demean_first, const int32_t* hyper_idx, const int32_t* nsamples, int* wmap_id);
+
+/* One evaluation of the compiled logp_forw_func(q) of a geometry-mode seismic problem for each of B chains:
+ * q [B, n_params] -> logpts [B, n_out], like [B].  Chains whose source leaves the GF store are reported
+ * (BEATGPU_E_INDEX; their logpts are NaN) -- the reference raises (beat/heart.py:3659-3662).                */
+int beatgpu_geom_loglike_batch(beatgpu_ctx* ctx, int B, const double* q, double* logpts, double* like);
+int beatgpu_geom_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q_dev, double* logpts_dev, double* like_dev);
+
+/* Forward model only: heart.seis_synthetics(..., outmode="array") for B chains: synthetics [B, nt, ns].        */
+int beatgpu_geom_synthetics_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* q, double* synthetics);
+
 /* Diagnostics (not on the product path): measured ceiling of the access pattern the GF stacking uses.  Gathers
  * pseudo-random rows of row_bytes (multiple of 16, <= 16384) from a zero-filled working set of ws_bytes with
  * mode 0 = one warp-wide 16-byte-per-lane load per row (gf_stack_chunk_kernel's pattern), mode 1 = one bulk

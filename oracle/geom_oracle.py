@@ -221,7 +221,8 @@ def store_nodes(store, depth, distance, interpolation):
 def component_weights(m6, azi, bazi, tazi, tdip):
     """[pyrocko] gf.meta.DiscretizedMTSource.make_weights (scheme 'elastic10') folded with the sensor orientation
     of gf.Target (north = ca*cd, east = sa*cd, down = sd of the target's azimuth/dip): weight of each of the 10
-    GF components in the seismogram of one target."""
+    GF components in the seismogram of one target (factors below 1e-15 in magnitude are dropped, as pyrocko's
+    ``nonzero`` does, so a vertical sensor reads the down seismogram only)."""
     sa, ca = math.sin(azi * d2r), math.cos(azi * d2r)
     sa2, ca2 = math.sin(2.0 * azi * d2r), math.cos(2.0 * azi * d2r)
     sb, cb = math.sin(bazi * d2r - math.pi), math.cos(bazi * d2r - math.pi)
@@ -237,6 +238,8 @@ def component_weights(m6, azi, bazi, tazi, tdip):
     fn = math.cos(tazi * d2r) * math.cos(tdip * d2r)
     fe = math.sin(tazi * d2r) * math.cos(tdip * d2r)
     fd = math.sin(tdip * d2r)
+    # [pyrocko] seismosizer.VectorRule.apply_: a base seismogram enters only if nonzero(factor, eps=1e-15)
+    fn, fe, fd = (f if abs(f) > 1e-15 else 0.0 for f in (fn, fe, fd))
     W = np.zeros(NCOMP)
     for g, wn, we in zip(G_NE, w_n, w_e):
         W[g] = fn * wn + fe * we

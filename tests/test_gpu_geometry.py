@@ -1,0 +1,263 @@
+"""GPU parity tests of the geometry-mode (point-source) seismic path -- BASELINE config 2, SURVEY rows a12 / f5 --
+through the C-ABI (beatgpu_geom_*), against oracle/geom_oracle.py on the same seeded inputs.
+
+Tolerances: synthetics ``atol = rtol = 5e-6`` relative to the largest synthetic amplitude (the reference's own
+tolerance for stacked synthetics, test/test_ffi_gfstacking.py:49-58; the GF sum accumulates in float32 like pyrocko's
+store, so summation order shows at the 1e-7 level); log-likelihoods ``rtol 1e-5`` (north-star tolerance).
+"""
+import numpy as np
+import pytest
+
+from beat_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import geom_oracle
+    return geom_oracle
+
+
+def _engine(gprob, **kw):
+    from beat_b200.geometry import BatchedGeometryLogLike
+    return BatchedGeometryLogLike.from_problem(gprob, device=0, **kw)
+
+
+def _points(gprob, Q):
+    return [S.split_point(gprob, q) for q in Q]
+
+
+def _with_data(gprob, noise="exponential"):
+    O = _oracle()
+    q0 = S.draw_chains(gprob, 1, seed=1)[0]
+    S.attach_geometry_data(gprob, O.geometry_synthetics(gprob, S.split_point(gprob, q0)), noise=noise)
+    return gprob
+
+
+def _assert_synth_close(got, ref):
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got, ref, rtol=5e-6, atol=5e-6 * scale)
+
+
+@pytest.mark.parametrize("interpolation", ["multilinear", "nearest_neighbor"])
+def test_synthetics_match_oracle(interpolation):
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=4, interpolation=interpolation, seed=21)
+    Q = S.draw_chains(gprob, 24, seed=3)
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    assert got.shape == ref.shape == (24, 12, 40)
+    _assert_synth_close(got, ref)
+
+
+@pytest.mark.parametrize("noise", ["exponential", "variance", "dense"])
+def test_loglike_matches_oracle(noise):
+    """exponential -> bidiagonal weights (fused streaming misfit), variance -> diagonal, dense -> residuals + DMMA GEMM."""
+    O = _oracle()
+    gprob = _with_data(S.make_geometry_problem(n_stations=3, seed=31), noise=noise)
+    Q = S.draw_chains(gprob, 40, seed=4)
+    Q[0] = S.draw_chains(gprob, 1, seed=1)[0]                  # the point the data were made from (smallest residuals)
+    ev = _engine(gprob)
+    logpts, like = ev(Q)
+    ev.close()
+    ref = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    np.testing.assert_allclose(logpts, ref, rtol=1e-5)
+    np.testing.assert_allclose(like, ref.sum(axis=1), rtol=1e-5)
+
+
+def test_hp_specific_and_single_channel():
+    O = _oracle()
+    gprob = _with_data(S.make_geometry_problem(n_stations=5, channels=("Z",), hp_specific=True, seed=41))
+    Q = S.draw_chains(gprob, 16, seed=5)
+    ev = _engine(gprob)
+    logpts, like = ev(Q)
+    one = ev.logp_forw_func(Q[3])
+    ev.close()
+    ref = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    np.testing.assert_allclose(logpts, ref, rtol=1e-5)
+    np.testing.assert_allclose(one[0], ref[3], rtol=1e-5)
+    np.testing.assert_allclose(one[1], ref[3].sum(), rtol=1e-5)
+
+
+def test_stf_edge_cases():
+    """duration 0 (one STF point), durations that put tmin/tmax exactly between grid points, long STF."""
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=2, duration_bounds=(0.0, 20.0), seed=51)
+    Q = S.draw_chains(gprob, 12, seed=6)
+    od, ot = gprob["offsets"]["duration"], gprob["offsets"]["time"]
+    Q[0, od] = 0.0
+    Q[1, od], Q[1, ot] = 0.25, 0.25                             # tmin_stf/deltat = 0.5: rint ties to even
+    Q[2, od], Q[2, ot] = 0.5, -0.75
+    Q[3, od] = 20.0
+    Q[4, od], Q[4, ot] = 1e-9, 1.0
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    _assert_synth_close(got, ref)
+
+
+@pytest.mark.parametrize("filterer", [
+    [],
+    [dict(kind="bandpass", order=4, lower_corner=0.02, upper_corner=0.5)],
+    [dict(kind="stepwise", order=2, lower_corner=0.05, upper_corner=0.3)],
+    [dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)],
+    [dict(kind="stepwise", order=3, lower_corner=0.02, upper_corner=0.6), dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)],
+])
+def test_filters(filterer):
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=2, filterer=filterer, seed=61)
+    Q = S.draw_chains(gprob, 8, seed=7)
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    _assert_synth_close(got, ref)
+
+
+def test_chop_a_d_applies_the_taper_flanks():
+    """chop bounds (a, d) keep the raised-cosine flanks (taper_filter_traces' plotting mode, heart.py:4242-4318)."""
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=2, ns=40, seed=71)
+    wm = gprob["wavemaps"][0]
+    wm["chop_bounds"] = ("a", "d")
+    wm["ns"] = 50                                               # (17.5 + 7.5) s at 2 Hz
+    Q = S.draw_chains(gprob, 6, seed=8)
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    ev.close()
+    ref = []
+    for p in _points(gprob, Q):
+        src = O.point_to_source(gprob, p)
+        rows = []
+        for t in range(wm["nt"]):
+            raw, itmin = O.seismogram(gprob, wm, t, src)
+            rows.append(O.post_process(wm, t, raw, itmin, chop_bounds=("a", "d")))
+        ref.append(np.vstack(rows))
+    ref = np.array(ref)
+    assert got.shape == ref.shape
+    assert np.all(ref[:, :, 0] == 0.0) and np.any(ref[:, :, 2] != 0.0)
+    _assert_synth_close(got, ref)
+
+
+def test_source_outside_store_raises_and_marks_nan():
+    gprob = _with_data(S.make_geometry_problem(n_stations=2, seed=81))
+    Q = S.draw_chains(gprob, 8, seed=9)
+    Q[5, gprob["offsets"]["depth"]] = 500.0                     # km: far below the store's deepest source
+    ev = _engine(gprob)
+    with pytest.raises(IndexError):
+        ev(Q)
+    import torch
+    q_dev = torch.from_numpy(Q).cuda()
+    logpts, like = ev.eval_device(q_dev)
+    torch.cuda.synchronize()
+    ev.ctx.index_violations()                                   # reset the counter
+    lp = logpts.cpu().numpy()
+    assert np.all(np.isnan(lp[5])) and np.all(np.isfinite(np.delete(lp, 5, axis=0)))
+    ev.close()
+
+
+def test_device_entry_matches_host_entry_and_fixed_variables():
+    import torch
+    O = _oracle()
+    gprob = _with_data(S.make_geometry_problem(n_stations=3, seed=91))
+    Q = S.draw_chains(gprob, 32, seed=10)
+    ev = _engine(gprob)
+    lp_host, like_host = ev(Q)
+    lp_dev, like_dev = ev.eval_device(torch.from_numpy(Q).cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(lp_dev.cpu().numpy(), lp_host)
+    np.testing.assert_array_equal(like_dev.cpu().numpy(), like_host)
+    ev.close()
+    # same problem with strike and the hyperparameter held fixed (offset -1 -> value from the fixed vector)
+    fixed = np.zeros(9 + gprob["n_hypers"])
+    fixed[3], fixed[9] = 77.0, 1.25
+    keep = [v for v, _ in gprob["var_order"] if v not in ("strike", "hypers")]
+    g2 = dict(gprob)
+    g2["offsets"] = {v: i for i, v in enumerate(keep)}
+    g2["n_params"] = len(keep)
+    g2["fixed"] = fixed
+    Q2 = np.ascontiguousarray(Q[:, [gprob["offsets"][v] for v in keep]])
+    ev2 = _engine(g2)
+    lp2, _ = ev2(Q2)
+    ev2.close()
+    Qf = Q.copy()
+    Qf[:, gprob["offsets"]["strike"]] = 77.0
+    Qf[:, gprob["offsets"]["hypers"]] = 1.25
+    ref = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Qf)])
+    np.testing.assert_allclose(lp2, ref, rtol=1e-5)
+
+
+def test_seis_synthesizer_op_single_point_and_batch():
+    """Calling convention of the reference Op (beat/pytensorf.py:215-302): dict of named variables in,
+    (synthetics, tmins) out."""
+    from beat_b200.geometry import ArrivalTaper, SeisSynthesizer
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=2, seed=101)
+    wm = gprob["wavemaps"][0]
+    op = SeisSynthesizer(gprob["store"], gprob["event"], dict(lats=wm["lats"], lons=wm["lons"], azimuths=wm["azimuths"], dips=wm["dips"]),
+                         ArrivalTaper(*wm["taper"]), wm["arrival_times"], wm["filterer"], pre_stack_cut=True,
+                         interpolation=wm["interpolation"])
+    assert op.infer_shape() == [(6, 40), (6,)]
+    Q = S.draw_chains(gprob, 5, seed=11)
+    p = S.split_point(gprob, Q[0])
+    synths, tmins = op({k: v for k, v in p.items() if k != "hypers"})
+    _assert_synth_close(synths, O.geometry_synthetics(gprob, p))
+    np.testing.assert_allclose(tmins, wm["arrival_times"] + wm["taper"][1])
+    batch = {v: Q[:, gprob["offsets"][v]] for v, _ in gprob["var_order"] if v != "hypers"}
+    sb, tb = op(batch)
+    assert sb.shape == (5, 6, 40) and tb.shape == (5, 6)
+    _assert_synth_close(sb[0], synths)
+    op.close()
+    with pytest.raises(NotImplementedError):
+        SeisSynthesizer(gprob["store"], gprob["event"], dict(lats=wm["lats"], lons=wm["lons"], azimuths=wm["azimuths"], dips=wm["dips"]),
+                        ArrivalTaper(*wm["taper"]), wm["arrival_times"], wm["filterer"], pre_stack_cut=False)
+
+
+def test_argument_errors():
+    from beat_b200.lib import Context
+    gprob = S.make_geometry_problem(n_stations=1, seed=111)
+    ev = _engine(gprob)
+    with pytest.raises(Exception, match="not uploaded"):
+        ev(S.draw_chains(gprob, 2))
+    with pytest.raises(ValueError):
+        ev(np.zeros((2, 3)))
+    # a wavemap whose declared sample count does not match the taper
+    wm = gprob["wavemaps"][0]
+    with pytest.raises(ValueError, match="chops to"):
+        ev.ctx.geom_add_wavemap(ev.store_id, 39, "multilinear", wm["lats"], wm["lons"], wm["azimuths"], wm["dips"], wm["arrival_times"],
+                                wm["taper"], ("b", "c"), [], wm["hyper_idx"], wm["nsamples"])
+    with pytest.raises(ValueError, match="a < b < c < d"):
+        ev.ctx.geom_add_wavemap(ev.store_id, 40, "multilinear", wm["lats"], wm["lons"], wm["azimuths"], wm["dips"], wm["arrival_times"],
+                                (0.0, -1.0, 2.0, 3.0), ("b", "c"), [], wm["hyper_idx"], wm["nsamples"])
+    ev.close()
+    # finite-fault and geometry wavemaps do not mix in one context
+    ctx = Context(0)
+    ctx.add_wavemap(2, 8, "nearest_neighbor", None, np.zeros(2, np.int32), np.full(2, 8, np.int32))
+    st = gprob["store"]
+    sid = ctx.geom_upload_store(st["traces"], st["itmin"], st["nsamples"], st["z0"], st["dz"], st["x0"], st["dx"], st["deltat"])
+    with pytest.raises(ValueError, match="one context per mode"):
+        ctx.geom_add_wavemap(sid, 40, "multilinear", wm["lats"], wm["lons"], wm["azimuths"], wm["dips"], wm["arrival_times"],
+                             wm["taper"], ("b", "c"), [], wm["hyper_idx"], wm["nsamples"])
+    ctx.close()
+
+
+def test_long_window_c2_shape_spot_check():
+    """One station x 3 components with config-2 sized windows (2048 samples + flanks): the 9-accumulator
+    instantiation of the delay-and-sum kernel and ~100 KB of shared memory per CTA."""
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=1, ns=2048, taper=(-34.0, -24.0, 1000.0, 1010.0), nrec=2300, lead=60.0,
+                                    dist_range=(2000e3, 2100e3), dx=20e3, seed=121,
+                                    filterer=[dict(kind="stepwise", order=4, lower_corner=0.005, upper_corner=0.2)])
+    gprob = _with_data(gprob)
+    Q = S.draw_chains(gprob, 6, seed=12)
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    logpts, _ = ev(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    _assert_synth_close(got, ref)
+    refl = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    np.testing.assert_allclose(logpts, refl, rtol=1e-5)
