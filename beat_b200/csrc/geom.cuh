@@ -39,7 +39,7 @@ constexpr int kGeomMaxNodes = 4;               // multilinear vicinity in (sourc
 constexpr int kGeomMaxRows = kGeomMaxNodes * kGeomNComp;
 constexpr int kGeomMaxStf = 64;                // STF points on the time grid (duration <= 63 * deltat)
 constexpr int kGeomThreads = 256;
-constexpr int kGeomHalfRows = 5;               // rows per pipeline half
+constexpr int kGeomHalfRows = 4;               // rows per pipeline half (8 slots of ~9 KB: three CTAs per SM at config-2 size)
 constexpr int kGeomMaxSec = 3;                 // IIR sections in cascade
 constexpr int kGeomMaxOrder = 8;
 
@@ -277,10 +277,11 @@ struct __align__(16) RowInfo {
 template <int ACC>
 __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs a)
 {
-    extern __shared__ __align__(128) unsigned char geom_smem[];
-    float* slots = (float*)geom_smem;                                             // [2][kGeomHalfRows][slot_floats]
-    float* comb = slots + 2 * kGeomHalfRows * a.slot_floats;                      // [slot_floats]
+    extern __shared__ __align__(128) float slots[];                               // [2][kGeomHalfRows][slot_floats]
+    float* comb = slots;                                                          // slot 0 is reused once all rows are consumed
     __shared__ RowInfo rows[kGeomMaxRows];
+    __shared__ RowInfo cand[kGeomMaxRows];
+    __shared__ unsigned char s_valid[kGeomMaxRows];
     __shared__ __align__(8) uint64_t bar[2];
     __shared__ float s_amp[kGeomMaxStf];
     __shared__ double red[kGeomThreads / 32];
@@ -296,51 +297,58 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     const int ncomb = n_raw + n_stf - 1;
     const int m0 = a.rcv_itmin[r] - cp.id0 - (n_stf - 1);                         // sample (rel. to source origin) of comb[0]
 
-    if (tid < kGeomMaxStf) s_amp[tid] = cp.amp[tid];
-    if (tid == 0) {
-        int n = 0;
-        for (int i = 0; i < kGeomMaxNodes; ++i) {
-            const int node = rp.node[i];
-            if (node < 0) continue;
-            for (int g = 0; g < kGeomNComp; ++g) {
-                // component -> (kind, slot): north/east use g = 0,1,2,8,3,4; down uses g = 5,6,7,9
-                int kind, k;
-                switch (g) {
-                    case 0: kind = 0; k = 0; break;  case 1: kind = 0; k = 1; break;  case 2: kind = 0; k = 2; break;
-                    case 8: kind = 0; k = 3; break;  case 3: kind = 0; k = 4; break;  case 4: kind = 0; k = 5; break;
-                    case 5: kind = 1; k = 0; break;  case 6: kind = 1; k = 1; break;  case 7: kind = 1; k = 2; break;
-                    default: kind = 1; k = 3; break;
-                }
-                RowInfo ri;
-                ri.kind = kind;
-                ri.w0 = rp.nw[i] * (kind == 0 ? rp.wn[k] : rp.wd[k]);
-                ri.w1 = kind == 0 ? rp.nw[i] * rp.we[k] : 0.f;
-                if (ri.w0 == 0.f && ri.w1 == 0.f) continue;
-                const long rec = (long)node * kGeomNComp + g;
-                const int it_rec = a.store.itmin[rec];
-                ri.nrec = a.store.nsamp[rec];
-                ri.rel = m0 - it_rec;
-                const int jlo = min(max(ri.rel, 0), ri.nrec - 1), jhi = min(max(ri.rel + ncomb - 1, 0), ri.nrec - 1);
-                ri.clamp = (ri.rel < 0 || ri.rel + ncomb - 1 > ri.nrec - 1) ? 1 : 0;
-                ri.ja = jlo & ~3;
-                const int jb = (int)min((long)a.store.ld, (long)((jhi + 4) & ~3));
-                ri.bytes = (jb - ri.ja) * 4;
-                ri.src = rec * a.store.ld + ri.ja;
-                rows[n++] = ri;
-            }
+    if (tid >= 64 && tid < 64 + kGeomMaxStf) s_amp[tid - 64] = cp.amp[tid - 64];
+    // row table: one thread per (node, component) candidate, so the record headers are fetched in parallel
+    if (tid < kGeomMaxRows) {
+        const int i = tid / kGeomNComp, g = tid % kGeomNComp;
+        const int node = rp.node[i];
+        bool valid = node >= 0;
+        if (valid) {
+            // component -> (kind, slot): north/east use g = 0,1,2,8,3,4; down uses g = 5,6,7,9
+            const int kind = (g >= 5 && g != 8) ? 1 : 0;
+            const int k = kind == 0 ? (g < 3 ? g : (g == 8 ? 3 : g + 1)) : (g == 9 ? 3 : g - 5);
+            RowInfo ri;
+            ri.kind = kind;
+            ri.w0 = rp.nw[i] * (kind == 0 ? rp.wn[k] : rp.wd[k]);
+            ri.w1 = kind == 0 ? rp.nw[i] * rp.we[k] : 0.f;
+            valid = !(ri.w0 == 0.f && ri.w1 == 0.f);
+            const long rec = (long)node * kGeomNComp + g;
+            const int it_rec = a.store.itmin[rec];
+            ri.nrec = a.store.nsamp[rec];
+            ri.rel = m0 - it_rec;
+            const int jlo = min(max(ri.rel, 0), ri.nrec - 1), jhi = min(max(ri.rel + ncomb - 1, 0), ri.nrec - 1);
+            ri.clamp = (ri.rel < 0 || ri.rel + ncomb - 1 > ri.nrec - 1) ? 1 : 0;
+            ri.ja = jlo & ~3;
+            const int jb = (int)min((long)a.store.ld, (long)((jhi + 4) & ~3));
+            ri.bytes = (jb - ri.ja) * 4;
+            ri.src = rec * a.store.ld + ri.ja;
+            cand[tid] = ri;
         }
-        s_nrows = n;
+        s_valid[tid] = valid ? 1 : 0;
+    }
+    if (tid == 0) {
         mbar_init(&bar[0], 1);
         mbar_init(&bar[1], 1);
         mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid < kGeomMaxRows) {                                                     // compact, keeping (node, component) order
+        int pos = 0;
+        for (int j = 0; j < tid; ++j) pos += s_valid[j];
+        if (s_valid[tid]) rows[pos] = cand[tid];
+        if (tid == kGeomMaxRows - 1) s_nrows = pos + s_valid[tid];
     }
     __syncthreads();
     const int nrows = s_nrows;
     const int nbatch = (nrows + kGeomHalfRows - 1) / kGeomHalfRows;
 
     float acc_n[ACC], acc_e[ACC], acc_d[ACC];
-#pragma unroll
-    for (int u = 0; u < ACC; ++u) acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
+    int cidx[ACC];                        // comb index of accumulator u, clamped into the window: the loops below are branch-free,
+#pragma unroll                            // accumulators past the window re-add its last sample and are never read
+    for (int u = 0; u < ACC; ++u) {
+        acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
+        cidx[u] = min(tid + u * kGeomThreads, ncomb - 1);
+    }
 
     auto issue = [&](int nb) {                                                    // thread 0 only
         const int h = nb & 1, r0 = nb * kGeomHalfRows, r1 = min(nrows, r0 + kGeomHalfRows);
@@ -361,36 +369,33 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         ok = __syncthreads_and(ok);                                               // uniform: a lost copy must not split the CTA
         if (!ok) break;
         const int r0 = nb * kGeomHalfRows, r1 = min(nrows, r0 + kGeomHalfRows);
-        {
-            for (int i = r0; i < r1; ++i) {
-                const RowInfo ri = rows[i];
-                const float* s = slots + ((long)h * kGeomHalfRows + (i - r0)) * a.slot_floats;
-                const int off = ri.rel - ri.ja;
-                if (!ri.clamp) {
-                    if (ri.kind == 0) {
-#pragma unroll
-                        for (int u = 0; u < ACC; ++u) {
-                            const int cc = tid + u * kGeomThreads;
-                            if (cc < ncomb) { const float x = s[cc + off]; acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]); }
-                        }
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < ACC; ++u) {
-                            const int cc = tid + u * kGeomThreads;
-                            if (cc < ncomb) acc_d[u] = fmaf(ri.w0, s[cc + off], acc_d[u]);
-                        }
-                    }
-                } else {                                                          // repeat the record's first / last value
+        for (int i = r0; i < r1; ++i) {
+            const RowInfo ri = rows[i];
+            const float* s = slots + (h * kGeomHalfRows + (i - r0)) * a.slot_floats;
+            if (!ri.clamp) {                                                      // window inside the record: s[c + off]
+                const char* so = (const char*)(s + (ri.rel - ri.ja));             // byte offsets: one add per element
+                if (ri.kind == 0) {
 #pragma unroll
                     for (int u = 0; u < ACC; ++u) {
-                        const int cc = tid + u * kGeomThreads;
-                        if (cc < ncomb) {
-                            const int j = min(max(cc + ri.rel, 0), ri.nrec - 1) - ri.ja;
-                            const float x = s[j];
-                            if (ri.kind == 0) { acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]); }
-                            else acc_d[u] = fmaf(ri.w0, x, acc_d[u]);
-                        }
+                        const float x = *(const float*)(so + 4 * cidx[u]);
+                        acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]);
                     }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, *(const float*)(so + 4 * cidx[u]), acc_d[u]);
+                }
+            } else {                                                              // repeat the record's first / last value
+                const float* so = s - ri.ja;
+                const int hi = ri.nrec - 1;
+                if (ri.kind == 0) {
+#pragma unroll
+                    for (int u = 0; u < ACC; ++u) {
+                        const float x = so[min(max(cidx[u] + ri.rel, 0), hi)];
+                        acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, so[min(max(cidx[u] + ri.rel, 0), hi)], acc_d[u]);
                 }
             }
         }
@@ -409,10 +414,13 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         }
         __syncthreads();
         double lsum = 0.0;
-        for (int i = tid; i < n_raw; i += kGeomThreads) {
+        float* dst = a.rawT + (((long)t * a.n4 + (tid >> 2)) * a.B + c) * 4 + (tid & 3);     // sample i = tid + 256 m
+        const long dstep = (long)(kGeomThreads / 4) * a.B * 4;
+        const float* cw = comb + (n_stf - 1) + tid;
+        for (int i = tid; i < n_raw; i += kGeomThreads, dst += dstep, cw += kGeomThreads) {
             float v = 0.f;
-            for (int k = 0; k < n_stf; ++k) v = fmaf(s_amp[k], comb[i + (n_stf - 1) - k], v);
-            a.rawT[(((long)t * a.n4 + (i >> 2)) * a.B + c) * 4 + (i & 3)] = v;
+            for (int k = 0; k < n_stf; ++k) v = fmaf(s_amp[k], cw[-k], v);
+            *dst = v;
             lsum += (double)v;
         }
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);

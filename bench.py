@@ -466,6 +466,12 @@ def _run_gpu_arm(args):
         peak, peak_src = _pk["hbm_gbs"], _pk["source"]
         bytes_launch = algorithmic_bytes_per_eval(a, args.store, args.interpolation) * B
         k_ms = float(np.mean(stack_ms))
+        try:
+            row_bytes = min(16384, max(16, (a["ns"] * (4 if args.store == "f32" else 8)) // 16 * 16))
+            gather_peak = max(ev.ctx.probe_gather(0, 30 << 20, row_bytes, 2048, 3) for _ in range(2))
+        except Exception as e:  # diagnostics only
+            log("gather probe failed: %s" % e)
+            gather_peak = None
         achieved = bytes_launch / (k_ms / 1e3) / 1e9
         traffic, tnote, l2_bytes = None, None, None
         tpath = os.path.join(ROOT, "profiles", "stack_kernel_traffic.json")
@@ -499,7 +505,11 @@ def _run_gpu_arm(args):
                          "l2_fabric": {"bytes_per_launch": l2_bytes,
                                        "achieved_GBps": (l2_bytes / (k_ms / 1e3) / 1e9) if l2_bytes else None,
                                        "peak_GBps": n_sm * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else None,
-                                       "peak_source": "n_sm x 64 B/clk x measured SM clock"},
+                                       "peak_source": "n_sm x 64 B/clk x measured SM clock",
+                                       # measured live: pseudo-random 480-byte rows out of a 30 MB (L2-resident) working
+                                       # set with the kernel's own access pattern (csrc/probe.cuh)
+                                       "measured_gather_peak_GBps": gather_peak,
+                                       "frac_of_measured_gather_peak": (achieved / gather_peak) if gather_peak else None},
                          "note": tnote},
         }
         if cpu_info is not None:
