@@ -342,13 +342,12 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     const int nrows = s_nrows;
     const int nbatch = (nrows + kGeomHalfRows - 1) / kGeomHalfRows;
 
+    // Accumulator u of a thread belongs to comb index tid + 256 u.  The loops below are branch-free: indices past the
+    // window (>= ncomb) read whatever lies behind it in shared memory (the ring is padded so that this stays in
+    // bounds) and those accumulators are never read.
     float acc_n[ACC], acc_e[ACC], acc_d[ACC];
-    int cidx[ACC];                        // comb index of accumulator u, clamped into the window: the loops below are branch-free,
-#pragma unroll                            // accumulators past the window re-add its last sample and are never read
-    for (int u = 0; u < ACC; ++u) {
-        acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
-        cidx[u] = min(tid + u * kGeomThreads, ncomb - 1);
-    }
+#pragma unroll
+    for (int u = 0; u < ACC; ++u) acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
 
     auto issue = [&](int nb) {                                                    // thread 0 only
         const int h = nb & 1, r0 = nb * kGeomHalfRows, r1 = min(nrows, r0 + kGeomHalfRows);
@@ -373,29 +372,29 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
             const RowInfo ri = rows[i];
             const float* s = slots + (h * kGeomHalfRows + (i - r0)) * a.slot_floats;
             if (!ri.clamp) {                                                      // window inside the record: s[c + off]
-                const char* so = (const char*)(s + (ri.rel - ri.ja));             // byte offsets: one add per element
+                const float* so = s + (ri.rel - ri.ja) + tid;                     // one LDS [R + imm] per element
                 if (ri.kind == 0) {
 #pragma unroll
                     for (int u = 0; u < ACC; ++u) {
-                        const float x = *(const float*)(so + 4 * cidx[u]);
+                        const float x = so[u * kGeomThreads];
                         acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]);
                     }
                 } else {
 #pragma unroll
-                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, *(const float*)(so + 4 * cidx[u]), acc_d[u]);
+                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, so[u * kGeomThreads], acc_d[u]);
                 }
             } else {                                                              // repeat the record's first / last value
                 const float* so = s - ri.ja;
-                const int hi = ri.nrec - 1;
+                const int hi = ri.nrec - 1, j0 = tid + ri.rel;
                 if (ri.kind == 0) {
 #pragma unroll
                     for (int u = 0; u < ACC; ++u) {
-                        const float x = so[min(max(cidx[u] + ri.rel, 0), hi)];
+                        const float x = so[min(max(j0 + u * kGeomThreads, 0), hi)];
                         acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]);
                     }
                 } else {
 #pragma unroll
-                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, so[min(max(cidx[u] + ri.rel, 0), hi)], acc_d[u]);
+                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, so[min(max(j0 + u * kGeomThreads, 0), hi)], acc_d[u]);
                 }
             }
         }
@@ -461,8 +460,12 @@ struct GeomFilterArgs {
 };
 
 // MODE 0: fused misfit with band width <= 1; MODE 1: fused misfit with band width <= 8; MODE 2: write synthetics / residuals
+// Register budget: with NSEC*ORD <= 8 filter states the kernel fits 48 registers, i.e. 14 CTAs of 96 threads = 1344
+// threads per SM, so that the 192 000 traces of config 2 are resident in ONE wave (at 56 registers and 128-thread CTAs
+// they needed 1.13 waves and the tail nearly doubled the time).
+constexpr int kFilterThreads = 96;
 template <int NSEC, int ORD, int MODE>
-__global__ void __launch_bounds__(128) trace_filter_misfit_kernel(GeomFilterArgs a)
+__global__ void __launch_bounds__(kFilterThreads) __maxnreg__((NSEC * ORD <= 8 && MODE != 1) ? 48 : 128) trace_filter_misfit_kernel(GeomFilterArgs a)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)a.nt * a.B) return;

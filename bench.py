@@ -564,16 +564,19 @@ def run_c2_llk(args):
     ctx.close()
 
 
-def c2_problem(quick=False):
+def c2_problem(quick=False, ragged=False):
     """BASELINE config 2: DC point source, 32 stations x 3 components x 2048 samples (2 Hz, b..c = 1024 s), stepwise
     Butterworth filter, Toeplitz (exponential) covariance.  Synthetic type-A GF store (10 components), ~0.6 GB > L2."""
     from beat_b200 import synthetic
     if quick:
         return synthetic.make_geometry_problem(n_stations=4, seed=7)
+    # default: every record spans the windows that can be asked of it (what a store built for the wavemap provides);
+    # --ragged: records of uneven length that start late / end early, so most rows take the end-value-repeating path
+    span = dict(nrec=2300, lead=60.0, ragged=True) if ragged else dict(nrec=2400, lead=90.0, ragged=False)
     return synthetic.make_geometry_problem(
-        n_stations=32, ns=2048, taper=(-34.0, -24.0, 1000.0, 1010.0), nrec=2300, lead=60.0, dist_range=(2000e3, 4000e3),
+        n_stations=32, ns=2048, taper=(-34.0, -24.0, 1000.0, 1010.0), dist_range=(2000e3, 4000e3),
         dx=4e3, dz=2.5e3, depth_range_km=(5.0, 30.0), duration_bounds=(0.0, 10.0), seed=7,
-        filterer=[dict(kind="stepwise", order=4, lower_corner=0.005, upper_corner=0.2)])
+        filterer=[dict(kind="stepwise", order=4, lower_corner=0.005, upper_corner=0.2)], **span)
 
 
 def load_peaks():
@@ -603,7 +606,7 @@ def run_c2(args):
     dev = torch.device("cuda", 0)
     B = args.chains if args.chains != 4000 else 2000
     log("building the config-2 problem")
-    gprob = c2_problem(args.quick)
+    gprob = c2_problem(args.quick, args.ragged)
     wm = gprob["wavemaps"][0]
     ev = BatchedGeometryLogLike.from_problem(gprob, device=0, upload_data=False)
     q_true = synthetic.draw_chains(gprob, 1, seed=1)
@@ -652,6 +655,7 @@ def run_c2(args):
             "higher_is_better": True, "dtype": "f64 (GF sum in f32 like the store)", "data": "synthetic",
             "config": {"workload": "C2 seismic DC point source: %d stations x 3 components x %d samples, %s, stepwise Butterworth "
                                    "order 4, exponential covariance" % (wm["nt"] // 3, wm["ns"], wm["interpolation"]),
+                       "gf_records": "ragged (end values repeated inside most windows)" if args.ragged else "span every window",
                        "chains_per_gpu": B, "gf_store_MB": gprob["store"]["traces"].nbytes / 1e6,
                        "l2": "q rotates between steps; raw-trace scratch %.1f GB > L2" % (B * wm["nt"] * 2200 * 4 / 1e9)},
             "e2e": {"value": B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(Qs[0].nbytes), "d2h_bytes_per_step": int(lp_pin.numel() * 8 + lk_pin.numel() * 8)},
@@ -688,6 +692,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--noise", default="exponential", choices=["exponential", "variance", "dense"],
                     help="data covariance structure (exponential = BASELINE config; dense = full non-Toeplitz, for the record)")
+    ap.add_argument("--ragged", action="store_true", help="config c2: GF records of uneven span (exercises the end-value path)")
     ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5", "c2llk", "c2"], help="c3 = BASELINE.json metric; c4/c5 for the record")
     args = ap.parse_args()
     global CONFIG, NOISE
