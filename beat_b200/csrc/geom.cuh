@@ -39,7 +39,7 @@ constexpr int kGeomMaxNodes = 4;               // multilinear vicinity in (sourc
 constexpr int kGeomMaxRows = kGeomMaxNodes * kGeomNComp;
 constexpr int kGeomMaxStf = 64;                // STF points on the time grid (duration <= 63 * deltat)
 constexpr int kGeomThreads = 256;
-constexpr int kGeomHalfRows = 4;               // rows per pipeline half (8 slots of ~9 KB: three CTAs per SM at config-2 size)
+constexpr int kGeomMaxHalfRows = 4;            // rows per pipeline half: template parameter HALF (3 or 4)
 constexpr int kGeomMaxSec = 3;                 // IIR sections in cascade
 constexpr int kGeomMaxOrder = 8;
 
@@ -274,16 +274,20 @@ struct __align__(16) RowInfo {
     int clamp;                                 // window leaves the record: indices must be clamped (repeat end values)
 };
 
-template <int ACC>
+// HALF rows per pipeline half: 2*HALF slots of ~9 KB at config-2 size -> HALF = 4: 72 KB, three CTAs per SM;
+// HALF = 3: 54 KB, four CTAs per SM (BEATGPU_GEOM_HALF selects; measurements in profiles/README.md).
+template <int ACC, int HALF>
 __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs a)
 {
-    extern __shared__ __align__(128) float slots[];                               // [2][kGeomHalfRows][slot_floats]
-    float* comb = slots;                                                          // slot 0 is reused once all rows are consumed
+    extern __shared__ __align__(128) float slots[];                               // [2][HALF][slot_floats]
+    float* comb = slots + 4;                                                      // slot 0 is reused once all rows are consumed; 4 zero guard floats in front
     __shared__ RowInfo rows[kGeomMaxRows];
-    __shared__ RowInfo cand[kGeomMaxRows];
+    // candidate table (before compaction) lives at the start of the ring (>= 2304 B for any window): the bulk copies
+    // that overwrite it are issued by thread 0 behind a fence.proxy.async after the compaction has been barriered
+    RowInfo* cand = reinterpret_cast<RowInfo*>(slots);
     __shared__ unsigned char s_valid[kGeomMaxRows];
     __shared__ __align__(8) uint64_t bar[2];
-    __shared__ float s_amp[kGeomMaxStf];
+    __shared__ __align__(16) float s_amp[kGeomMaxStf + 4];                        // zero padded to a multiple of 4 taps
     __shared__ double red[kGeomThreads / 32];
     __shared__ int s_nrows;
 
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     const int ncomb = n_raw + n_stf - 1;
     const int m0 = a.rcv_itmin[r] - cp.id0 - (n_stf - 1);                         // sample (rel. to source origin) of comb[0]
 
-    if (tid >= 64 && tid < 64 + kGeomMaxStf) s_amp[tid - 64] = cp.amp[tid - 64];
+    if (tid >= 64 && tid < 64 + kGeomMaxStf + 4) s_amp[tid - 64] = (tid - 64 < kGeomMaxStf) ? cp.amp[tid - 64] : 0.f;
     // row table: one thread per (node, component) candidate, so the record headers are fetched in parallel
     if (tid < kGeomMaxRows) {
         const int i = tid / kGeomNComp, g = tid % kGeomNComp;
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     }
     __syncthreads();
     const int nrows = s_nrows;
-    const int nbatch = (nrows + kGeomHalfRows - 1) / kGeomHalfRows;
+    const int nbatch = (nrows + HALF - 1) / HALF;
 
     // Accumulator u of a thread belongs to comb index tid + 256 u.  The loops below are branch-free: indices past the
     // window (>= ncomb) read whatever lies behind it in shared memory (the ring is padded so that this stays in
@@ -350,16 +354,16 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     for (int u = 0; u < ACC; ++u) acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
 
     auto issue = [&](int nb) {                                                    // thread 0 only
-        const int h = nb & 1, r0 = nb * kGeomHalfRows, r1 = min(nrows, r0 + kGeomHalfRows);
+        const int h = nb & 1, r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
         uint32_t total = 0;
         for (int i = r0; i < r1; ++i) total += (uint32_t)rows[i].bytes;
         mbar_arrive_expect_tx(&bar[h], total);
         for (int i = r0; i < r1; ++i)
-            tma_load_1d(slots + ((long)h * kGeomHalfRows + (i - r0)) * a.slot_floats, a.store.traces + rows[i].src,
+            tma_load_1d(slots + ((long)h * HALF + (i - r0)) * a.slot_floats, a.store.traces + rows[i].src,
                         (uint32_t)rows[i].bytes, &bar[h]);
     };
 
-    if (tid == 0 && nbatch > 0) issue(0);
+    if (tid == 0 && nbatch > 0) { fence_proxy_async(); issue(0); }
     bool ok = true;
     for (int nb = 0; nb < nbatch; ++nb) {
         if (tid == 0 && nb + 1 < nbatch) { fence_proxy_async(); issue(nb + 1); }  // half (nb+1)&1 was released by the barrier below
@@ -367,10 +371,10 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         ok = mbar_wait_bounded(&bar[h], (uint32_t)(nb >> 1) & 1u, 1u << 20);
         ok = __syncthreads_and(ok);                                               // uniform: a lost copy must not split the CTA
         if (!ok) break;
-        const int r0 = nb * kGeomHalfRows, r1 = min(nrows, r0 + kGeomHalfRows);
+        const int r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
         for (int i = r0; i < r1; ++i) {
             const RowInfo ri = rows[i];
-            const float* s = slots + (h * kGeomHalfRows + (i - r0)) * a.slot_floats;
+            const float* s = slots + (h * HALF + (i - r0)) * a.slot_floats;
             if (!ri.clamp) {                                                      // window inside the record: s[c + off]
                 const float* so = s + (ri.rel - ri.ja) + tid;                     // one LDS [R + imm] per element
                 if (ri.kind == 0) {
@@ -403,6 +407,8 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     if (!ok) { if (tid == 0) atomicAdd(a.err, 1u); return; }
 
     // ---- per target channel of this receiver: sensor projection, STF convolution, mean, store
+    if (tid < 4) slots[tid] = 0.f;                                                // guard: taps padded with zero amplitude read comb[-1..-3]
+    const int n_tap4 = (n_stf + 3) >> 2;
     for (int q = a.rcv_first[r]; q < a.rcv_first[r + 1]; ++q) {
         const int t = a.tgt_of[q];
         const float fn = a.tgt_f[3 * t], fe = a.tgt_f[3 * t + 1], fd = a.tgt_f[3 * t + 2];
@@ -417,8 +423,16 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         const long dstep = (long)(kGeomThreads / 4) * a.B * 4;
         const float* cw = comb + (n_stf - 1) + tid;
         for (int i = tid; i < n_raw; i += kGeomThreads, dst += dstep, cw += kGeomThreads) {
-            float v = 0.f;
-            for (int k = 0; k < n_stf; ++k) v = fmaf(s_amp[k], cw[-k], v);
+            float v0 = 0.f, v1 = 0.f;                                             // raw[i] = sum_k amp[k] comb[i + n_stf-1 - k], four taps per step
+            for (int k4 = 0; k4 < n_tap4; ++k4) {
+                const float4 am = *(const float4*)(s_amp + 4 * k4);
+                const float* cp4 = cw - 4 * k4;
+                v0 = fmaf(am.x, cp4[0], v0);
+                v1 = fmaf(am.y, cp4[-1], v1);
+                v0 = fmaf(am.z, cp4[-2], v0);
+                v1 = fmaf(am.w, cp4[-3], v1);
+            }
+            const float v = v0 + v1;
             *dst = v;
             lsum += (double)v;
         }
@@ -460,10 +474,11 @@ struct GeomFilterArgs {
 };
 
 // MODE 0: fused misfit with band width <= 1; MODE 1: fused misfit with band width <= 8; MODE 2: write synthetics / residuals
-// Register budget: with NSEC*ORD <= 8 filter states the kernel fits 48 registers, i.e. 14 CTAs of 96 threads = 1344
+// Register budget: with NSEC*ORD <= 8 filter states the kernel fits 48 registers, i.e. 21 CTAs of 64 threads = 1344
 // threads per SM, so that the 192 000 traces of config 2 are resident in ONE wave (at 56 registers and 128-thread CTAs
-// they needed 1.13 waves and the tail nearly doubled the time).
-constexpr int kFilterThreads = 96;
+// they needed 1.13 waves and the tail nearly doubled the time; 96-thread CTAs are limited to 13 per SM by the
+// register allocation granularity).
+constexpr int kFilterThreads = 64;
 template <int NSEC, int ORD, int MODE>
 __global__ void __launch_bounds__(kFilterThreads) __maxnreg__((NSEC * ORD <= 8 && MODE != 1) ? 48 : 128) trace_filter_misfit_kernel(GeomFilterArgs a)
 {
@@ -520,8 +535,10 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__((NSEC * ORD <= 8 &
         }
     };
 
+    float4 nxt = __ldcs(src);
     for (int i0 = 0; i0 < iend; i0 += 4) {
-        const float4 v4 = __ldcs(src + (long)(i0 >> 2) * a.B);
+        const float4 v4 = nxt;
+        if (i0 + 4 < iend) nxt = __ldcs(src + (long)((i0 >> 2) + 1) * a.B);       // prefetch the next four samples
         const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
