@@ -474,13 +474,14 @@ struct GeomFilterArgs {
 };
 
 // MODE 0: fused misfit with band width <= 1; MODE 1: fused misfit with band width <= 8; MODE 2: write synthetics / residuals
-// Register budget: with NSEC*ORD <= 8 filter states the kernel fits 48 registers, i.e. 21 CTAs of 64 threads = 1344
-// threads per SM, so that the 192 000 traces of config 2 are resident in ONE wave (at 56 registers and 128-thread CTAs
-// they needed 1.13 waves and the tail nearly doubled the time; 96-thread CTAs are limited to 13 per SM by the
-// register allocation granularity).
-constexpr int kFilterThreads = 64;
-template <int NSEC, int ORD, int MODE>
-__global__ void __launch_bounds__(kFilterThreads) __maxnreg__((NSEC * ORD <= 8 && MODE != 1) ? 48 : 128) trace_filter_misfit_kernel(GeomFilterArgs a)
+// The kernel is FP64-pipe work (about 24 DFMA-class instructions per sample and thread) that only runs at rate when the
+// loads are off the critical path: raw samples are prefetched one float4 ahead and the data / weight / taper operands
+// of a block of four samples are fetched together at the top of the block (measured: 1.9 ms -> see profiles/README.md
+// with per-sample loads at config-2 size, long-scoreboard stalls 56 % of all stall cycles).
+constexpr int kFilterThreads = 128;
+// CAP: register cap (80 -> 6 CTAs per SM instead of 5 at the uncapped 94; BEATGPU_FILTER_CAP selects, see profiles/README.md)
+template <int NSEC, int ORD, int MODE, int CAP>
+__global__ void __launch_bounds__(kFilterThreads) __maxnreg__(CAP) trace_filter_misfit_kernel(GeomFilterArgs a)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)a.nt * a.B) return;
@@ -540,6 +541,23 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__((NSEC * ORD <= 8 &
         const float4 v4 = nxt;
         if (i0 + 4 < iend) nxt = __ldcs(src + (long)((i0 >> 2) + 1) * a.B);       // prefetch the next four samples
         const float xs[4] = {v4.x, v4.y, v4.z, v4.w};
+        // operands of the window samples of this block, all requested before the arithmetic starts (indices clamped into
+        // the window; a value fetched for a sample outside it is never used)
+        const int k0 = i0 - ibeg;
+        double cd[4], ct[4], cw0[4], cw1[4];
+        if (k0 > -4) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int kc = min(max(k0 + e, 0), ns - 1);
+                cd[e] = dat ? dat[kc] : 0.0;
+                ct[e] = tap ? tap[kc] : 1.0;
+                if (MODE == 0) {
+                    const int kk = max(kc - bw, 0);
+                    cw0[e] = Wt[kk];
+                    cw1[e] = bw ? Wt[ns + kk] : 0.0;
+                }
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int i = i0 + e;
@@ -555,9 +573,17 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__((NSEC * ORD <= 8 &
                 }
                 const int k = i - ibeg;
                 if (k >= 0) {
-                    if (tap) x *= tap[k];
-                    if (MODE == 2) a.out[((long)c * a.nt + t) * ns + k] = a.out_resid ? dat[k] - x : x;
-                    else push_resid(k, dat[k] - x);
+                    if (tap) x *= ct[e];
+                    if (MODE == 2) a.out[((long)c * a.nt + t) * ns + k] = a.out_resid ? cd[e] - x : x;
+                    else if (MODE == 1) push_resid(k, cd[e] - x);
+                    else {                                               // band width <= 1 with the prefetched weights
+                        const double rk = cd[e] - x;
+                        if (bw == 0) { const double zz = cw0[e] * rk; quad = fma(zz, zz, quad); }
+                        else {
+                            sh[0] = sh[1]; sh[1] = rk;
+                            if (k >= 1) { const double zz = fma(cw1[e], sh[1], cw0[e] * sh[0]); quad = fma(zz, zz, quad); }
+                        }
+                    }
                 }
             }
         }
