@@ -147,7 +147,7 @@ struct beatgpu_ctx {
     void *d_rplan = nullptr, *d_cplan = nullptr, *d_rawT = nullptr, *d_gmean = nullptr;
     size_t g_rplan_bytes = 0, g_cplan_bytes = 0, g_raw_bytes = 0, g_mean_bytes = 0;
     unsigned int* d_gerr = nullptr;
-    int filter_cap = 0;             // BEATGPU_FILTER_CAP=80: register-capped filter kernel (6 CTAs per SM)
+    int filter_cap = 80;            // BEATGPU_FILTER_CAP: 80 = register-capped filter kernel (6 CTAs per SM, measured faster), 0 = uncapped
     int geom_half = 3;              // BEATGPU_GEOM_HALF: rows per pipeline half of the delay-and-sum kernel (3 or 4; 3 measured faster)
 };
 
@@ -492,7 +492,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_PERSISTENT")) c->persistent = atoi(e) != 0;
     if (const char* e = getenv("BEATGPU_STACK_MODE")) c->stack_mode = (strcmp(e, "fused") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_GEO_MODE")) c->geo_mode = (strcmp(e, "simple") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
-    if (const char* e = getenv("BEATGPU_FILTER_CAP")) { int v = atoi(e); if (v == 80) c->filter_cap = v; }
+    if (const char* e = getenv("BEATGPU_FILTER_CAP")) { int v = atoi(e); if (v == 80 || v == 0) c->filter_cap = v; }
     if (const char* e = getenv("BEATGPU_GEOM_HALF")) { int v = atoi(e); if (v == 3 || v == 4) c->geom_half = v; }
     if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) c->chunk_patches = v; }
     *out = c;
