@@ -15,6 +15,12 @@ one chain at a time, exactly in the order the reference evaluates it:
             DynamicTarget.update_target_times  beat/heart.py:457-477
     residuals / multivariate_normal_chol      beat/models/seismic.py:819-828, beat/models/distributions.py:72-140
 
+PINNED (BEAT side): tests/golden/geometry_golden.npz holds synthetics produced by the reference's OWN
+heart.seis_synthetics / get_phase_taperer / update_target_times / post_process_trace / Filter.apply, imported from
+/root/reference (tests/golden/make_geometry_golden.py; pyrocko's Trace and engine replaced by stand-ins): the window the
+reference puts on each target, the order and arguments of highpass / lowpass / extend / taper / chop, the stacking and
+the returned tmins are the reference's, and this module reproduces them bit for bit.
+
 PARITY UNPINNED for the part below the engine.process() call: the arithmetic of the seismogram synthesis, the
 filters and the taper lives in the third-party package **pyrocko** (>= 2023.10.11, reference pyproject.toml:35),
 which is neither vendored under /root/reference nor installed in this image, and the reference ships no golden

@@ -186,3 +186,36 @@ def test_host_mirrors():
         ArrivalTaper(-15.0, -10.0, 50.1, 55.0).check_sample_rate_consistency(0.5)
     with pytest.raises(ValueError, match="a < b < c < d"):
         ArrivalTaper(0.0, -1.0, 2.0, 3.0)
+
+
+GOLDEN_CASES = {
+    "stepwise_ml": (dict(n_stations=3, seed=201), ("b", "c")),
+    "bandpass_nn": (dict(n_stations=2, seed=202, interpolation="nearest_neighbor",
+                         filterer=[dict(kind="bandpass", order=3, lower_corner=0.02, upper_corner=0.5)]), ("b", "c")),
+    "bandstop_ad": (dict(n_stations=2, seed=203, channels=("Z", "E"),
+                         filterer=[dict(kind="stepwise", order=2, lower_corner=0.05, upper_corner=0.6),
+                                   dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)]), ("a", "d")),
+}
+
+
+def load_geometry_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geometry_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_oracle_reproduces_reference_driven_golden(name):
+    """tests/golden/geometry_golden.npz was produced by the reference's OWN heart.seis_synthetics / post_process_trace /
+    Filter.apply / update_target_times (tests/golden/make_geometry_golden.py; pyrocko's Trace and engine replaced by
+    stand-ins): the oracle's composition of window, filter, taper and chop must reproduce it exactly."""
+    g = load_geometry_golden()
+    kw, chop = GOLDEN_CASES[name]
+    gprob = S.make_geometry_problem(**kw)
+    wm = gprob["wavemaps"][0]
+    Q, ref = g[name + "_Q"], g[name + "_synths"]
+    for i, q in enumerate(Q):
+        src = O.point_to_source(gprob, S.split_point(gprob, q))
+        mine = np.vstack([O.post_process(wm, t, *O.seismogram(gprob, wm, t, src), chop_bounds=chop) for t in range(wm["nt"])])
+        np.testing.assert_allclose(mine, ref[i], rtol=1e-12, atol=1e-18)
+    tm = wm["arrival_times"] + dict(zip("abcd", wm["taper"]))[chop[0]]
+    np.testing.assert_allclose(g[name + "_tmins"][0], tm)

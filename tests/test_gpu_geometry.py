@@ -302,3 +302,20 @@ def test_smc_driver_runs_on_the_geometry_engine():
         assert abs(post[c] - ref) <= 1e-5 * abs(ref) + 1e-3
     assert (out["population"] >= lower).all() and (out["population"] <= upper).all()
     ev.close()
+
+
+@pytest.mark.parametrize("name", ["stepwise_ml", "bandpass_nn", "bandstop_ad"])
+def test_cuda_matches_reference_driven_golden(name):
+    """CUDA synthetics against tests/golden/geometry_golden.npz -- produced by the reference's own
+    heart.seis_synthetics control flow (make_geometry_golden.py); committed fixture, no oracle in the loop."""
+    from test_geometry_cpu import GOLDEN_CASES, load_geometry_golden
+    g = load_geometry_golden()
+    kw, chop = GOLDEN_CASES[name]
+    gprob = S.make_geometry_problem(**kw)
+    wm = gprob["wavemaps"][0]
+    wm["chop_bounds"] = chop
+    wm["ns"] = int(g[name + "_synths"].shape[2])
+    ev = _engine(gprob)
+    got = ev.get_synthetics(g[name + "_Q"])
+    ev.close()
+    _assert_synth_close(got, g[name + "_synths"])
