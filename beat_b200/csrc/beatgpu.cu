@@ -65,6 +65,12 @@ struct GeomWaveMap {
     float* d_tgt_f = nullptr;
     int *d_tgt_nraw = nullptr, *d_tgt_ibeg = nullptr;
     double* d_taper = nullptr;      // nullptr: all factors are 1 (chop between b and c)
+    // station corrections (time_shift hierarchical): windows follow arrival + shift of the chain
+    bool has_station = false;
+    double *d_rcv_arrival = nullptr, *d_tgt_arrival = nullptr;
+    int *d_rcv_station = nullptr, *d_tgt_station = nullptr, *d_tgt_rcv = nullptr;
+    double abcd[4] = {0, 0, 0, 0};
+    int chop_lo = 1, chop_hi = 2, nraw_cap = 0;
     int nsec = 1, ord = 1, demean = 0;
     double fb[kGeomMaxSec][kGeomMaxOrder + 1], fa[kGeomMaxSec][kGeomMaxOrder + 1];
 };
@@ -523,6 +529,7 @@ void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
     for (auto& g : ctx->gwmaps) {
         cudaFree(g.d_rcv_lat); cudaFree(g.d_rcv_lon); cudaFree(g.d_rcv_itmin); cudaFree(g.d_rcv_nraw); cudaFree(g.d_rcv_first);
         cudaFree(g.d_tgt_of); cudaFree(g.d_tgt_f); cudaFree(g.d_tgt_nraw); cudaFree(g.d_tgt_ibeg); cudaFree(g.d_taper);
+        cudaFree(g.d_rcv_arrival); cudaFree(g.d_tgt_arrival); cudaFree(g.d_rcv_station); cudaFree(g.d_tgt_station); cudaFree(g.d_tgt_rcv);
     }
     cudaFree(ctx->d_gfixed); cudaFree(ctx->d_rplan); cudaFree(ctx->d_cplan); cudaFree(ctx->d_rawT); cudaFree(ctx->d_gmean);
     cudaFree(ctx->d_gerr);

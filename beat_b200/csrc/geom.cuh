@@ -58,6 +58,8 @@ struct __align__(16) RcvPlan {
     int node[kGeomMaxNodes];                   // iz * nx + ix, or -1
     float nw[kGeomMaxNodes];                   // interpolation weight
     float wn[6], we[6], wd[4];                 // 'elastic10' weights of the north / east / down seismograms (moment included)
+    int itmin, nraw;                           // window the engine computes (moves with a station correction)
+    int pad0, pad1;
 };
 
 struct __align__(16) ChainPlan {
@@ -74,6 +76,13 @@ struct GeomPlanArgs {
     const double* rcv_lat; const double* rcv_lon;                                   // [nr]
     GeomStoreDev store;
     int interpolation;
+    // window of every receiver: fixed (rcv_itmin / rcv_nraw from the host) or, with station corrections, recomputed per
+    // chain from arrival + time_shift (SeisSynthesizer.perform, pytensorf.py:248-252; update_target_times, heart.py:474-477)
+    const int* rcv_itmin; const int* rcv_nraw;                                      // [nr]
+    const double* rcv_arrival; const int* rcv_station;                              // [nr]; rcv_station nullptr = no corrections
+    ChainVar tshift;                                                                // time_shifts [n_time_shifts]
+    double ta, tb, td;                                                              // taper a, b, d relative to the arrival
+    int nraw_cap;                                                                   // largest window the scratch holds
     RcvPlan* rplan;                            // [B, nr]
     ChainPlan* cplan;                          // [B]
     unsigned char* chain_bad;                  // [B]
@@ -237,6 +246,19 @@ __global__ void __launch_bounds__(128) geom_plan_kernel(GeomPlanArgs a)
                     if (wa[i] != 0.0 && wb[j] != 0.0) { rp.node[n] = ia[i] * a.store.nx + ib[j]; rp.nw[n] = (float)(wa[i] * wb[j]); ++n; }
         }
     }
+    // ---- window
+    rp.pad0 = rp.pad1 = 0;
+    if (a.rcv_station) {
+        const double at = a.rcv_arrival[r] + a.tshift.p[(long)c * a.tshift.stride + a.rcv_station[r]];
+        const double wa = at + a.ta, wb = at + a.tb, wd_ = at + a.td;
+        const double tol = 2.0 * (wb - wa);
+        const double lo = floor((wa - tol) / a.store.deltat), hi = ceil((wd_ + tol) / a.store.deltat);
+        if (!isfinite(at) || !(fabs(lo) < 2.0e9) || !(hi - lo + 1.0 <= (double)a.nraw_cap)) { bad = true; rp.itmin = 0; rp.nraw = 1; }
+        else { rp.itmin = (int)lo; rp.nraw = (int)(hi - lo) + 1; }
+    } else {
+        rp.itmin = a.rcv_itmin[r];
+        rp.nraw = a.rcv_nraw[r];
+    }
     if (oob && !bad) atomicAdd(a.violations, 1ULL);
     if (oob || bad) a.chain_bad[c] = 1;
     a.rplan[idx] = rp;
@@ -251,8 +273,6 @@ struct GeomSumArgs {
     const RcvPlan* rplan;                      // [B, nr]
     const ChainPlan* cplan;                    // [B]
     const unsigned char* chain_bad;            // [B]
-    const int* rcv_itmin;                      // [nr] first sample of the computed window (absolute index, floor(tmin/deltat))
-    const int* rcv_nraw;                       // [nr] samples in the window
     const int* rcv_first;                      // [nr + 1] CSR into tgt_of
     const int* tgt_of;                         // target index of each channel of a receiver
     const float* tgt_f;                        // [nt, 3] sensor factors (north, east, down) = (ca*cd, sa*cd, sd) of azimuth/dip
@@ -297,9 +317,9 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     const ChainPlan& cp = a.cplan[c];
     const RcvPlan& rp = a.rplan[(long)c * a.nr + r];
     const int n_stf = cp.n_stf;
-    const int n_raw = a.rcv_nraw[r];
+    const int n_raw = rp.nraw;                                                    // window from the plan (absolute first sample rp.itmin)
     const int ncomb = n_raw + n_stf - 1;
-    const int m0 = a.rcv_itmin[r] - cp.id0 - (n_stf - 1);                         // sample (rel. to source origin) of comb[0]
+    const int m0 = rp.itmin - cp.id0 - (n_stf - 1);                         // sample (rel. to source origin) of comb[0]
 
     if (tid >= 64 && tid < 64 + kGeomMaxStf + 4) s_amp[tid - 64] = (tid - 64 < kGeomMaxStf) ? cp.amp[tid - 64] : 0.f;
     // row table: one thread per (node, component) candidate, so the record headers are fetched in parallel
@@ -459,6 +479,10 @@ struct GeomFilterArgs {
     const int* tgt_nraw;                       // [nt]
     const int* tgt_ibeg;                       // [nt] first chopped sample within the raw window
     const double* taper;                       // [nt, ns] factors on the chopped samples, or nullptr
+    // station corrections: window, chop start and taper follow arrival + time_shift of the chain
+    const RcvPlan* rplan; const int* tgt_rcv; int nr;                               // rplan nullptr = fixed windows
+    const double* tgt_arrival; const int* tgt_station; ChainVar tshift;
+    double ta, tb, tc, td, dt; int chop_lo, chop_hi;
     // IIR cascade, coefficients normalised by a[0]; b[s][0..ORD], a[s][1..ORD] (a[s][0] unused), zero padded
     double fb[kGeomMaxSec][kGeomMaxOrder + 1];
     double fa[kGeomMaxSec][kGeomMaxOrder + 1];
@@ -492,8 +516,30 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__(CAP) trace_filter_
         return;
     }
     constexpr int MAXBW = MODE == 0 ? 1 : 8;
-    const int ns = a.ns, ibeg = a.tgt_ibeg[t];
-    const int iend = min(a.tgt_nraw[t], ibeg + ns);                 // nothing after the chop window is needed
+    const int ns = a.ns;
+    int ibeg, n_raw_t;
+    // station corrections: taper flanks evaluated on the fly (apply_costaper); h* = first sample index at / after a, b, c, d
+    int h_a = 0, h_b = 0, h_c = 0x7fffffff, h_d = 0x7fffffff;
+    double wa = 0.0, wb = 1.0, wc = 0.0, wd = 1.0, x0 = 0.0;
+    const bool dyn = a.rplan != nullptr;
+    if (dyn) {
+        const RcvPlan& rp = a.rplan[(long)c * a.nr + a.tgt_rcv[t]];
+        const double at = a.tgt_arrival[t] + a.tshift.p[(long)c * a.tshift.stride + a.tgt_station[t]];
+        wa = at + a.ta; wb = at + a.tb; wc = at + a.tc; wd = at + a.td;
+        x0 = (double)rp.itmin * a.dt;
+        n_raw_t = rp.nraw;
+        const double bounds[4] = {wa, wb, wc, wd};
+        ibeg = max(0, (int)floor((bounds[a.chop_lo] - x0) / a.dt));                   // Trace.chop, snap = (floor, floor)
+        const double nn = (double)n_raw_t;
+        h_a = (int)fmax(0.0, fmin(nn, ceil((wa - x0) / a.dt)));
+        h_b = (int)fmax(0.0, fmin(nn, ceil((wb - x0) / a.dt)));
+        h_c = (int)fmax(0.0, fmin(nn, ceil((wc - x0) / a.dt)));
+        h_d = (int)fmax(0.0, fmin(nn, ceil((wd - x0) / a.dt)));
+    } else {
+        ibeg = a.tgt_ibeg[t];
+        n_raw_t = a.tgt_nraw[t];
+    }
+    const int iend = min(n_raw_t, ibeg + ns);                       // nothing after the chop window is needed
     const double mu = a.demean ? a.mean[(long)c * a.nt + t] : 0.0;
     const float4* src = (const float4*)a.rawT + (long)t * a.n4 * a.B + c;
     const double* dat = a.data ? a.data + (long)t * ns : nullptr;
@@ -574,6 +620,13 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__(CAP) trace_filter_
                 const int k = i - ibeg;
                 if (k >= 0) {
                     if (tap) x *= ct[e];
+                    if (dyn && (i < h_b || i >= h_c)) {             // on a taper flank (at most the first sample for chop (b, c))
+                        double f;
+                        if (i < h_a || i >= h_d) f = 0.0;
+                        else if (i < h_b) f = 0.5 - 0.5 * cos((a.dt * (double)i - (wa - x0)) / (wb - wa) * CUDART_PI);
+                        else f = 0.5 + 0.5 * cos((a.dt * (double)i - (wc - x0)) / (wd - wc) * CUDART_PI);
+                        x *= f;
+                    }
                     if (MODE == 2) a.out[((long)c * a.nt + t) * ns + k] = a.out_resid ? cd[e] - x : x;
                     else if (MODE == 1) push_resid(k, cd[e] - x);
                     else {                                               // band width <= 1 with the prefetched weights

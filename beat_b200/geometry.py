@@ -100,13 +100,15 @@ def _sections(filterer, deltat):
     return secs
 
 
-def _layout_from_offsets(offsets, n_params, n_hypers):
+def _layout_from_offsets(offsets, n_params, n_hypers, n_time_shifts=0):
     L = GeomLayout()
     L.n_params = n_params
     for v in GEOM_VARS:
         setattr(L, "off_" + v, offsets.get(v, -1))
     L.off_hypers = offsets.get("hypers", -1)
     L.n_hypers = n_hypers
+    L.off_time_shifts = offsets.get("time_shifts", -1)
+    L.n_time_shifts = n_time_shifts
     return L
 
 
@@ -127,7 +129,8 @@ class BatchedGeometryLogLike:
         ctx = self.ctx
         st = gprob["store"]
         fixed = gprob.get("fixed")
-        ctx.geom_set_source(_layout_from_offsets(gprob["offsets"], gprob["n_params"], gprob["n_hypers"]), fixed,
+        ctx.geom_set_source(_layout_from_offsets(gprob["offsets"], gprob["n_params"], gprob["n_hypers"],
+                                                 gprob.get("n_time_shifts", 0)), fixed,
                             gprob["event"]["lat"], gprob["event"]["lon"], gprob.get("stf_anchor", -1.0))
         self.store_id = ctx.geom_upload_store(st["traces"], st["itmin"], st["nsamples"], st["z0"], st["dz"], st["x0"], st["dx"],
                                               st["deltat"])
@@ -138,7 +141,8 @@ class BatchedGeometryLogLike:
             ArrivalTaper(*taper).check_sample_rate_consistency(st["deltat"])
             wid = ctx.geom_add_wavemap(self.store_id, wm["ns"], wm["interpolation"], wm["lats"], wm["lons"], wm["azimuths"],
                                        wm["dips"], wm["arrival_times"], taper, wm.get("chop_bounds", ("b", "c")),
-                                       _sections(wm["filterer"], st["deltat"]), wm["hyper_idx"], wm["nsamples"])
+                                       _sections(wm["filterer"], st["deltat"]), wm["hyper_idx"], wm["nsamples"],
+                                       station_idx=wm.get("station_idx"))
             self.wmap_ids.append(wid)
             self._wm_shapes.append((wm["nt"], wm["ns"]))
             if upload_data and wm.get("data") is not None:
@@ -211,10 +215,11 @@ class SeisSynthesizer(object):
     ``(synthetics, tmins)`` -- [nt, ns] and [nt] (with a leading chain axis for a batch).  ``tmins`` are the taper's
     lower chop bound per target (beat/heart.py:3729), constant because the arrival times are fixed."""
 
-    __props__ = ("store", "event", "targets", "arrival_taper", "arrival_times", "filterer", "pre_stack_cut")
+    __props__ = ("store", "event", "targets", "arrival_taper", "arrival_times", "filterer", "pre_stack_cut",
+                 "station_corrections")
 
     def __init__(self, store, event, targets, arrival_taper, arrival_times, filterer, pre_stack_cut=True,
-                 interpolation="multilinear", stf_anchor=-1.0, chop_bounds=("b", "c"), device=0):
+                 station_corrections=False, interpolation="multilinear", stf_anchor=-1.0, chop_bounds=("b", "c"), device=0):
         if not pre_stack_cut:
             raise NotImplementedError("only pre_stack_cut=True (the reference's default) is implemented")
         self.store, self.event, self.targets = store, event, targets
@@ -226,41 +231,53 @@ class SeisSynthesizer(object):
         self.nt = len(targets["lats"])
         self.ns = self.arrival_taper.nsamples(1.0 / store["deltat"], self.chop_bounds)
         self.varnames = list(GEOM_VARS)
+        self.station_corrections = bool(station_corrections)
         offsets = {v: i for i, v in enumerate(GEOM_VARS)}
+        n_par, n_ts = len(GEOM_VARS), 0
+        if self.station_corrections:            # the Op receives one time_shift per target (pytensorf.py:248-252)
+            offsets["time_shifts"], n_ts = n_par, self.nt
+            n_par += n_ts
+        self._n_par = n_par
         self._ctx = Context(device)
-        self._ctx.geom_set_source(_layout_from_offsets(offsets, len(GEOM_VARS), 0), None, event["lat"], event["lon"], stf_anchor)
+        self._ctx.geom_set_source(_layout_from_offsets(offsets, n_par, 0, n_ts), None, event["lat"], event["lon"], stf_anchor)
         sid = self._ctx.geom_upload_store(store["traces"], store["itmin"], store["nsamples"], store["z0"], store["dz"],
                                           store["x0"], store["dx"], store["deltat"])
         self._wid = self._ctx.geom_add_wavemap(sid, self.ns, interpolation, targets["lats"], targets["lons"], targets["azimuths"],
                                                targets["dips"], self.arrival_times, self.arrival_taper.abcd(), self.chop_bounds,
                                                _sections(self.filterer, store["deltat"]), np.zeros(self.nt, np.int32),
-                                               np.full(self.nt, self.ns, np.int32))
+                                               np.full(self.nt, self.ns, np.int32),
+                                               station_idx=np.arange(self.nt, dtype=np.int32) if self.station_corrections else None)
 
     def infer_shape(self, fgraph=None, node=None, input_shapes=None):
         return [(self.nt, self.ns), (self.nt,)]                           # pytensorf.py:303-311
 
     def perform(self, node, inputs, output):
         point = {v: np.asarray(i, dtype=np.float64) for v, i in zip(self.varnames, inputs)}
-        sizes = {p.size for p in point.values()}
-        B = max(sizes)
+        shifts = point.pop("time_shift", None)
+        B = max(p.size for p in point.values())
         batched = any(p.ndim >= 1 and p.size > 1 for p in point.values())
-        Q = np.empty((B, len(GEOM_VARS)))
+        Q = np.zeros((B, self._n_par))
         for i, v in enumerate(GEOM_VARS):
             Q[:, i] = point[v].reshape(-1)
+        arrival = np.broadcast_to(self.arrival_times, (B, self.nt))
+        if self.station_corrections:
+            if shifts is None:
+                raise KeyError("time_shift")
+            Q[:, len(GEOM_VARS):] = shifts.reshape(-1, self.nt)
+            arrival = arrival + Q[:, len(GEOM_VARS):]
         synths = self._ctx.geom_synthetics_batch(self._wid, Q, self.nt, self.ns)
-        tmins = self.arrival_times + getattr(self.arrival_taper, self.chop_bounds[0])
+        tmins = arrival + getattr(self.arrival_taper, self.chop_bounds[0])       # heart.py:3729
         output[0][0] = synths if batched else synths[0]
-        output[1][0] = np.broadcast_to(tmins, (B, self.nt)).copy() if batched else tmins
+        output[1][0] = tmins.copy() if batched else tmins[0].copy()
 
     def __call__(self, inputs):
         """``inputs``: dict of named variables, as the reference's ``make_node`` takes (pytensorf.py:215-239)."""
-        self.varnames = [v for v in inputs.keys() if v in GEOM_VARS]
         missing = [v for v in GEOM_VARS if v not in inputs]
         if missing:
             raise KeyError("source variables missing: %s" % ", ".join(missing))
-        self.varnames = list(GEOM_VARS)
+        self.varnames = list(GEOM_VARS) + (["time_shift"] if self.station_corrections else [])
         out = [[None], [None]]
-        self.perform(None, [inputs[v] for v in GEOM_VARS], out)
+        self.perform(None, [inputs[v] for v in self.varnames], out)
         return out[0][0], out[1][0]
 
     def close(self):

@@ -60,7 +60,7 @@ class GeomLayout(C.Structure):
     """beatgpu_geom_layout (geometry-mode parameter vector -> DC source variables)."""
     _fields_ = [(n, C.c_int32) for n in (
         "n_params", "off_east_shift", "off_north_shift", "off_depth", "off_strike", "off_dip", "off_rake",
-        "off_magnitude", "off_time", "off_duration", "off_hypers", "n_hypers")]
+        "off_magnitude", "off_time", "off_duration", "off_hypers", "n_hypers", "off_time_shifts", "n_time_shifts")]
 
 
 GEOM_VARS = ("east_shift", "north_shift", "depth", "strike", "dip", "rake", "magnitude", "time", "duration")
@@ -106,7 +106,7 @@ _SIGNATURES = {
     "beatgpu_geom_upload_store": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                                             C.POINTER(C.c_int)]),
     "beatgpu_geom_add_wavemap": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
-                                           C.c_int, _P, _P, _P, C.c_int, _P, _P, C.POINTER(C.c_int)]),
+                                           C.c_int, _P, _P, _P, C.c_int, _P, _P, _P, C.POINTER(C.c_int)]),
     "beatgpu_geom_loglike_batch": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_geom_loglike_batch_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_geom_synthetics_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
@@ -394,7 +394,7 @@ class Context:
         return sid.value
 
     def geom_add_wavemap(self, store_id, ns, interpolation, lats, lons, azimuths, dips, arrival_times, taper_abcd,
-                         chop_bounds, sections, hyper_idx, nsamples):
+                         chop_bounds, sections, hyper_idx, nsamples, station_idx=None):
         """sections: [(b, a, demean), ...] as scipy.signal.butter returns them (demean only on the first)."""
         lats, lons, az, dp, at = (_f64(x) for x in (lats, lons, azimuths, dips, arrival_times))
         nt = lats.size
@@ -415,10 +415,12 @@ class Context:
             sa[i, :a.size] = a
         demean_first = int(bool(nsec and sections[0][2]))
         hidx, nsm = _i32(hyper_idx), _i32(nsamples)
+        sidx = None if station_idx is None else _i32(station_idx)
         wid = C.c_int()
         self._check(self._lib.beatgpu_geom_add_wavemap(
             self._h, store_id, nt, ns, INTERPOLATION[interpolation], _ptr(lats), _ptr(lons), _ptr(az), _ptr(dp), _ptr(at),
-            _ptr(abcd), lo, hi, nsec, _ptr(order), _ptr(sb), _ptr(sa), demean_first, _ptr(hidx), _ptr(nsm), C.byref(wid)))
+            _ptr(abcd), lo, hi, nsec, _ptr(order), _ptr(sb), _ptr(sa), demean_first, _ptr(sidx), _ptr(hidx), _ptr(nsm),
+            C.byref(wid)))
         return wid.value
 
     def geom_loglike_batch(self, Q):

@@ -235,19 +235,21 @@ int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms);
  * (un-vendored dependency, >= 2023.10.11): its published algorithm is restated, see csrc/geom.cuh and
  * oracle/geom_oracle.py.  Times are relative to the reference event's origin time.  Supported: one DC source per
  * wavemap, HalfSinusoid STF, GF component scheme 'elastic10', store type A (source depth x distance), pre_stack_cut
- * = True (the reference's default), time domain, no station corrections.  A context is either finite-fault or
+ * = True (the reference's default), time domain, station corrections.  A context is either finite-fault or
  * geometry mode.                                                                                            */
 
 /* Flat parameter vector -> source variables (pymc bijection over value_vars, beat/backend.py:147,163-165; variable
  * list beat/config.py:83-94 for DCSource + 'duration' of the STF, beat/utility.py:773-797).  Offset -1 = not
  * sampled: value taken from fixed[] in the canonical order [east_shift, north_shift, depth, strike, dip, rake,
- * magnitude, time, duration, hypers...].                                                                    */
+ * magnitude, time, duration, hypers..., time_shifts...].                                                    */
 typedef struct beatgpu_geom_layout {
     int32_t n_params;
     int32_t off_east_shift, off_north_shift, off_depth;      /* [km] (utility.adjust_point_units converts to m) */
     int32_t off_strike, off_dip, off_rake;                   /* [deg]                                            */
     int32_t off_magnitude, off_time, off_duration;
     int32_t off_hypers, n_hypers;
+    int32_t off_time_shifts, n_time_shifts;                  /* hierarchical station corrections [s] (time_shifts_<mapid>,
+                                                                beat/models/seismic.py:198-294); n = 0: none            */
 } beatgpu_geom_layout;
 /* event_lat/lon: origin the source's north/east shifts refer to (the reference event, beat/config.py:2045-2066);
  * stf_anchor: HalfSinusoidSTF.anchor, -1 in the reference (beat/config.py:2060).                             */
@@ -269,13 +271,17 @@ int beatgpu_geom_upload_store(beatgpu_ctx* ctx, const int64_t dims[4], double z0
  * (the likelihood uses 1, 2 = ["b", "c"], seismic.py:755), and the filter as a cascade of IIR sections exactly as
  * scipy.signal.butter returns them (Filter.apply, heart.py:377-392: stepwise = high-pass with demean, then
  * low-pass): sec_b / sec_a are [n_sections, 9] (zero padded), demean_first != 0 removes the trace mean before the
- * first section.  Targets sharing position and window are synthesised together.  Data and weights are uploaded
- * with beatgpu_upload_data / beatgpu_update_weights under the returned id.                                   */
+ * first section.  station_idx[n_targets] (or NULL) maps a target to its entry of the time_shifts hierarchical
+ * (wmap.station_correction_idxs; SeisSynthesizer.perform adds it to the arrival time, beat/pytensorf.py:248-252):
+ * the engine window, the chop and the taper then move with the chain's correction while the data stay put.
+ * Targets sharing position and window are synthesised together.  Data and weights are uploaded with
+ * beatgpu_upload_data / beatgpu_update_weights under the returned id.                                         */
 int beatgpu_geom_add_wavemap(beatgpu_ctx* ctx, int store_id, int n_targets, int n_samples, int interpolation,
                              const double* lats, const double* lons, const double* azimuths, const double* dips,
                              const double* arrival_times, const double taper_abcd[4], int chop_lo, int chop_hi,
                              int n_sections, const int32_t* sec_order, const double* sec_b, const double* sec_a,
-                             int demean_first, const int32_t* hyper_idx, const int32_t* nsamples, int* wmap_id);
+                             int demean_first, const int32_t* station_idx, const int32_t* hyper_idx,
+                             const int32_t* nsamples, int* wmap_id);
 
 /* One evaluation of the compiled logp_forw_func(q) of a geometry-mode seismic problem for each of B chains:
  * q [B, n_params] -> logpts [B, n_out], like [B].  Chains whose source leaves the GF store are reported

@@ -377,7 +377,7 @@ def post_process(wm, t, raw, itmin, chop_bounds=("b", "c")):
 def point_to_source(gprob, point):
     """utility.adjust_point_units (beat/utility.py:651-675: km -> m for the location variables) + update_source
     (:773-797; ``duration`` goes to the STF).  ``time`` is relative to the event origin."""
-    src = {k: float(np.asarray(v).ravel()[0]) for k, v in point.items() if k not in ("hypers",)}
+    src = {k: float(np.asarray(v).ravel()[0]) for k, v in point.items() if k not in ("hypers", "time_shifts")}
     for k in ("east_shift", "north_shift", "depth"):
         src[k] *= KM
     return src
@@ -386,6 +386,11 @@ def point_to_source(gprob, point):
 def geometry_synthetics(gprob, point, iw=0):
     """heart.seis_synthetics(..., outmode='array') for one wavemap and ONE source: [nt, ns] float64."""
     wm = gprob["wavemaps"][iw]
+    if wm.get("station_idx") is not None:
+        # SeisSynthesizer.perform (beat/pytensorf.py:248-252): arrival_times + time_shifts; the hierarchical is gathered per
+        # target with wmap.station_correction_idxs (beat/models/seismic.py:781-784).  Windows, taper and chop follow.
+        shifts = np.asarray(point["time_shifts"], dtype=np.float64)[wm["station_idx"]]
+        wm = dict(wm, arrival_times=np.asarray(wm["arrival_times"]) + shifts)
     src = point_to_source(gprob, point)
     rows = []
     for t in range(wm["nt"]):

@@ -186,6 +186,8 @@ def main():
         dict(name="bandstop_ad", kw=dict(n_stations=2, seed=203, channels=("Z", "E"),
                                          filterer=[dict(kind="stepwise", order=2, lower_corner=0.05, upper_corner=0.6),
                                                    dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)]), chop=("a", "d")),
+        # station corrections: SeisSynthesizer.perform hands arrival_times + time_shifts to seis_synthetics (pytensorf.py:248-252)
+        dict(name="station_corr", kw=dict(n_stations=3, seed=204, station_corrections=True), chop=("b", "c")),
     ]
     for case in cases:
         gprob = S.make_geometry_problem(**case["kw"])
@@ -205,21 +207,29 @@ def main():
         assert all(tg.response is None for tg in targets)
         Q = S.draw_chains(gprob, 4, seed=300 + len(out))
         synths_ref, tmins_ref = [], []
-        engine = Engine(gprob, wm)
         for q in Q:
-            src = types.SimpleNamespace(params=O.point_to_source(gprob, S.split_point(gprob, q)))
+            point = S.split_point(gprob, q)
+            arrival_times = np.array(wm["arrival_times"])
+            if wm.get("station_idx") is not None:
+                arrival_times = arrival_times + point["time_shifts"][wm["station_idx"]]
+            engine = Engine(gprob, dict(wm, arrival_times=arrival_times))
+            src = types.SimpleNamespace(params=O.point_to_source(gprob, point))
             synths, tmins = heart.seis_synthetics(
                 engine=engine, sources=[src], targets=targets, arrival_taper=ataper, wavename="any_P", filterer=filterer,
-                pre_stack_cut=True, arrival_times=np.array(wm["arrival_times"]), outmode="array", chop_bounds=list(case["chop"]))
+                pre_stack_cut=True, arrival_times=arrival_times, outmode="array", chop_bounds=list(case["chop"]))
             synths_ref.append(synths)
             tmins_ref.append(tmins)
         synths_ref, tmins_ref = np.array(synths_ref), np.array(tmins_ref)
         # the oracle's own composition must reproduce what the reference's control flow produced
         for i, q in enumerate(Q):
-            srcp = O.point_to_source(gprob, S.split_point(gprob, q))
-            mine = np.vstack([O.post_process(wm, t, *O.seismogram(gprob, wm, t, srcp), chop_bounds=case["chop"]) for t in range(wm["nt"])])
+            if case["chop"] == ("b", "c"):
+                mine = O.geometry_synthetics(gprob, S.split_point(gprob, q))
+            else:
+                srcp = O.point_to_source(gprob, S.split_point(gprob, q))
+                mine = np.vstack([O.post_process(wm, t, *O.seismogram(gprob, wm, t, srcp), chop_bounds=case["chop"]) for t in range(wm["nt"])])
             np.testing.assert_array_equal(mine, synths_ref[i])
-        np.testing.assert_allclose(tmins_ref[0], wm["arrival_times"] + dict(a=a, b=b, c=c, d=d)[case["chop"][0]])
+        if wm.get("station_idx") is None:
+            np.testing.assert_allclose(tmins_ref[0], wm["arrival_times"] + dict(a=a, b=b, c=c, d=d)[case["chop"][0]])
         assert ataper.nsamples(1.0 / wm["deltat"], list(case["chop"])) == synths_ref.shape[2]
         n = case["name"]
         out[n + "_Q"], out[n + "_synths"], out[n + "_tmins"] = Q, synths_ref, tmins_ref

@@ -195,6 +195,7 @@ GOLDEN_CASES = {
     "bandstop_ad": (dict(n_stations=2, seed=203, channels=("Z", "E"),
                          filterer=[dict(kind="stepwise", order=2, lower_corner=0.05, upper_corner=0.6),
                                    dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)]), ("a", "d")),
+    "station_corr": (dict(n_stations=3, seed=204, station_corrections=True), ("b", "c")),
 }
 
 
@@ -214,8 +215,12 @@ def test_oracle_reproduces_reference_driven_golden(name):
     wm = gprob["wavemaps"][0]
     Q, ref = g[name + "_Q"], g[name + "_synths"]
     for i, q in enumerate(Q):
-        src = O.point_to_source(gprob, S.split_point(gprob, q))
-        mine = np.vstack([O.post_process(wm, t, *O.seismogram(gprob, wm, t, src), chop_bounds=chop) for t in range(wm["nt"])])
+        point = S.split_point(gprob, q)
+        if chop == ("b", "c"):
+            mine = O.geometry_synthetics(gprob, point)
+        else:
+            src = O.point_to_source(gprob, point)
+            mine = np.vstack([O.post_process(wm, t, *O.seismogram(gprob, wm, t, src), chop_bounds=chop) for t in range(wm["nt"])])
         np.testing.assert_allclose(mine, ref[i], rtol=1e-12, atol=1e-18)
-    tm = wm["arrival_times"] + dict(zip("abcd", wm["taper"]))[chop[0]]
-    np.testing.assert_allclose(g[name + "_tmins"][0], tm)
+        shifts = point["time_shifts"][wm["station_idx"]] if wm.get("station_idx") is not None else 0.0
+        np.testing.assert_allclose(g[name + "_tmins"][i], wm["arrival_times"] + shifts + dict(zip("abcd", wm["taper"]))[chop[0]])

@@ -304,7 +304,7 @@ def test_smc_driver_runs_on_the_geometry_engine():
     ev.close()
 
 
-@pytest.mark.parametrize("name", ["stepwise_ml", "bandpass_nn", "bandstop_ad"])
+@pytest.mark.parametrize("name", ["stepwise_ml", "bandpass_nn", "bandstop_ad", "station_corr"])
 def test_cuda_matches_reference_driven_golden(name):
     """CUDA synthetics against tests/golden/geometry_golden.npz -- produced by the reference's own
     heart.seis_synthetics control flow (make_geometry_golden.py); committed fixture, no oracle in the loop."""
@@ -319,3 +319,38 @@ def test_cuda_matches_reference_driven_golden(name):
     got = ev.get_synthetics(g[name + "_Q"])
     ev.close()
     _assert_synth_close(got, g[name + "_synths"])
+
+
+def test_station_corrections():
+    """time_shift hierarchical (SeisSynthesizer.perform, beat/pytensorf.py:248-252): the engine window, the chop position
+    and the taper follow arrival + shift of the chain; data stay where prepare_data put them."""
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=3, station_corrections=True, corr_bounds=(-2.0, 2.0), seed=141)
+    q0 = S.draw_chains(gprob, 1, seed=1)[0]
+    q0[gprob["offsets"]["time_shifts"]:] = 0.0
+    S.attach_geometry_data(gprob, O.geometry_synthetics(gprob, S.split_point(gprob, q0)))
+    Q = S.draw_chains(gprob, 24, seed=15)
+    ots = gprob["offsets"]["time_shifts"]
+    Q[0] = q0
+    Q[1, ots:] = [0.5, -1.0, 1.5]                               # on the sampling grid
+    Q[2, ots:] = [0.25, -0.25, 0.1]                             # off the grid: floor-snapped chop, first sample on the taper flank
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    logpts, like = ev(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    _assert_synth_close(got, ref)
+    refl = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    _assert_logpts_close(gprob, Q, logpts, refl)
+    # the Op mirror takes one time_shift per target, like the reference Op
+    from beat_b200.geometry import ArrivalTaper, SeisSynthesizer
+    wm = gprob["wavemaps"][0]
+    op = SeisSynthesizer(gprob["store"], gprob["event"], dict(lats=wm["lats"], lons=wm["lons"], azimuths=wm["azimuths"], dips=wm["dips"]),
+                         ArrivalTaper(*wm["taper"]), wm["arrival_times"], wm["filterer"], station_corrections=True)
+    p = S.split_point(gprob, Q[2])
+    inputs = {k: v for k, v in p.items() if k not in ("hypers", "time_shifts")}
+    inputs["time_shift"] = p["time_shifts"][wm["station_idx"]]
+    synths, tmins = op(inputs)
+    _assert_synth_close(synths, ref[2])
+    np.testing.assert_allclose(tmins, wm["arrival_times"] + inputs["time_shift"] + wm["taper"][1])
+    op.close()
