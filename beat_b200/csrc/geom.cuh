@@ -504,7 +504,9 @@ struct GeomFilterArgs {
 // with per-sample loads at config-2 size, long-scoreboard stalls 56 % of all stall cycles).
 constexpr int kFilterThreads = 128;
 // CAP: register cap (80 -> 6 CTAs per SM instead of 5 at the uncapped 94; BEATGPU_FILTER_CAP selects, see profiles/README.md)
-template <int NSEC, int ORD, int MODE, int CAP>
+// DYN: station corrections -- window, chop start and taper flanks follow the chain's time shift (kept out of the common
+// instantiation: the extra state costs ~25 registers)
+template <int NSEC, int ORD, int MODE, int CAP, bool DYN>
 __global__ void __launch_bounds__(kFilterThreads) __maxnreg__(CAP) trace_filter_misfit_kernel(GeomFilterArgs a)
 {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -521,15 +523,15 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__(CAP) trace_filter_
     // station corrections: taper flanks evaluated on the fly (apply_costaper); h* = first sample index at / after a, b, c, d
     int h_a = 0, h_b = 0, h_c = 0x7fffffff, h_d = 0x7fffffff;
     double wa = 0.0, wb = 1.0, wc = 0.0, wd = 1.0, x0 = 0.0;
-    const bool dyn = a.rplan != nullptr;
+    constexpr bool dyn = DYN;
     if (dyn) {
         const RcvPlan& rp = a.rplan[(long)c * a.nr + a.tgt_rcv[t]];
         const double at = a.tgt_arrival[t] + a.tshift.p[(long)c * a.tshift.stride + a.tgt_station[t]];
         wa = at + a.ta; wb = at + a.tb; wc = at + a.tc; wd = at + a.td;
         x0 = (double)rp.itmin * a.dt;
         n_raw_t = rp.nraw;
-        const double bounds[4] = {wa, wb, wc, wd};
-        ibeg = max(0, (int)floor((bounds[a.chop_lo] - x0) / a.dt));                   // Trace.chop, snap = (floor, floor)
+        const double lower = a.chop_lo == 0 ? wa : (a.chop_lo == 1 ? wb : wc);
+        ibeg = max(0, (int)floor((lower - x0) / a.dt));                               // Trace.chop, snap = (floor, floor)
         const double nn = (double)n_raw_t;
         h_a = (int)fmax(0.0, fmin(nn, ceil((wa - x0) / a.dt)));
         h_b = (int)fmax(0.0, fmin(nn, ceil((wb - x0) / a.dt)));
