@@ -280,6 +280,7 @@ struct GeomSumArgs {
     int n4;                                    // float4 groups per raw trace
     float* rawT;                               // [nt, n4, B, 4] raw traces, chain-interleaved
     double* mean;                              // [B, nt] mean of each raw trace
+    int accumulate;                            // second and further sources: add to what the previous source left (heart.py:3719-3724)
     unsigned int* err;                         // bulk-copy time-outs (must stay 0)
 };
 
@@ -452,7 +453,8 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
                 v0 = fmaf(am.z, cp4[-2], v0);
                 v1 = fmaf(am.w, cp4[-3], v1);
             }
-            const float v = v0 + v1;
+            float v = v0 + v1;
+            if (a.accumulate) v += *dst;
             *dst = v;
             lsum += (double)v;
         }

@@ -100,7 +100,7 @@ def _sections(filterer, deltat):
     return secs
 
 
-def _layout_from_offsets(offsets, n_params, n_hypers, n_time_shifts=0):
+def _layout_from_offsets(offsets, n_params, n_hypers, n_time_shifts=0, n_sources=1):
     L = GeomLayout()
     L.n_params = n_params
     for v in GEOM_VARS:
@@ -109,6 +109,7 @@ def _layout_from_offsets(offsets, n_params, n_hypers, n_time_shifts=0):
     L.n_hypers = n_hypers
     L.off_time_shifts = offsets.get("time_shifts", -1)
     L.n_time_shifts = n_time_shifts
+    L.n_sources = n_sources
     return L
 
 
@@ -130,7 +131,7 @@ class BatchedGeometryLogLike:
         st = gprob["store"]
         fixed = gprob.get("fixed")
         ctx.geom_set_source(_layout_from_offsets(gprob["offsets"], gprob["n_params"], gprob["n_hypers"],
-                                                 gprob.get("n_time_shifts", 0)), fixed,
+                                                 gprob.get("n_time_shifts", 0), gprob.get("n_sources", 1)), fixed,
                             gprob["event"]["lat"], gprob["event"]["lon"], gprob.get("stf_anchor", -1.0))
         self.store_id = ctx.geom_upload_store(st["traces"], st["itmin"], st["nsamples"], st["z0"], st["dz"], st["x0"], st["dx"],
                                               st["deltat"])
@@ -152,7 +153,7 @@ class BatchedGeometryLogLike:
             a, b, c, d = taper
             for at in {(la, lo, at) for la, lo, at in zip(wm["lats"], wm["lons"], wm["arrival_times"])}:
                 n_raw = int(np.ceil((at[2] + d + 2 * (b - a)) / st["deltat"]) - np.floor((at[2] + a - 2 * (b - a)) / st["deltat"])) + 1
-                self._bytes_per_eval += (4 if wm["interpolation"] == "multilinear" else 1) * 10 * n_raw * 4
+                self._bytes_per_eval += gprob.get("n_sources", 1) * (4 if wm["interpolation"] == "multilinear" else 1) * 10 * n_raw * 4
         self.n_out = ctx.n_outputs()
         return self
 

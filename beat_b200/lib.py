@@ -60,7 +60,7 @@ class GeomLayout(C.Structure):
     """beatgpu_geom_layout (geometry-mode parameter vector -> DC source variables)."""
     _fields_ = [(n, C.c_int32) for n in (
         "n_params", "off_east_shift", "off_north_shift", "off_depth", "off_strike", "off_dip", "off_rake",
-        "off_magnitude", "off_time", "off_duration", "off_hypers", "n_hypers", "off_time_shifts", "n_time_shifts")]
+        "off_magnitude", "off_time", "off_duration", "off_hypers", "n_hypers", "off_time_shifts", "n_time_shifts", "n_sources")]
 
 
 GEOM_VARS = ("east_shift", "north_shift", "depth", "strike", "dip", "rake", "magnitude", "time", "duration")

@@ -251,7 +251,7 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
                           interpolation="multilinear", filterer=None, dist_range=(500e3, 700e3), shift_km=10.0,
                           depth_range_km=(2.0, 10.0), dz=2.0e3, dx=4.0e3, nrec=200, time_bounds=(-3.0, 3.0),
                           duration_bounds=(0.0, 6.0), seed=99, hp_specific=False, ragged=True, lead=10.0,
-                          station_corrections=False, corr_bounds=(-1.0, 1.0)):
+                          station_corrections=False, corr_bounds=(-1.0, 1.0), n_sources=1):
     """Synthetic geometry-mode seismic problem (one wavemap, one DC source).  ``data`` / weights are attached later by
     ``attach_geometry_data`` from synthetics of a reference point (tests: the oracle's; bench: the GPU engine's)."""
     rng = np.random.default_rng(seed)
@@ -281,7 +281,7 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
             codes.append("ST%02d.%s" % (s, ch))
     nt = len(lats)
     n_hypers = nt if hp_specific else 1
-    var_order = [(v, 1) for v in GEOM_VARS] + [("hypers", n_hypers)]
+    var_order = [(v, n_sources) for v in GEOM_VARS] + [("hypers", n_hypers)]     # pymc vectors of shape (n_sources,)
     if station_corrections:                   # one hierarchical time shift per station (seismic.py:198-294)
         var_order.append(("time_shifts", n_stations))
     offsets, o = {}, 0
@@ -302,6 +302,7 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
               station_idx=(np.repeat(np.arange(n_stations, dtype=np.int32), len(channels)) if station_corrections else None))
     return dict(mode="geometry", store=store, event=dict(lat=ev_lat, lon=ev_lon), stf_anchor=-1.0, var_order=var_order,
                 offsets=offsets, n_params=o, n_hypers=n_hypers, n_time_shifts=n_stations if station_corrections else 0,
+                n_sources=n_sources,
                 priors=priors, wavemaps=[wm], seed=seed)
 
 

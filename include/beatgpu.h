@@ -233,15 +233,15 @@ int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms);
  * (beat/heart.py:3564-3762) -> post_process_trace (:3466-3525) and the likelihood of
  * SeismicGeometryComposite.get_formula (beat/models/seismic.py:737-837).  The synthesis itself is pyrocko's
  * (un-vendored dependency, >= 2023.10.11): its published algorithm is restated, see csrc/geom.cuh and
- * oracle/geom_oracle.py.  Times are relative to the reference event's origin time.  Supported: one DC source per
- * wavemap, HalfSinusoid STF, GF component scheme 'elastic10', store type A (source depth x distance), pre_stack_cut
+ * oracle/geom_oracle.py.  Times are relative to the reference event's origin time.  Supported: DC sources (one or
+ * several, stacked), HalfSinusoid STF, GF component scheme 'elastic10', store type A (source depth x distance), pre_stack_cut
  * = True (the reference's default), time domain, station corrections.  A context is either finite-fault or
  * geometry mode.                                                                                            */
 
 /* Flat parameter vector -> source variables (pymc bijection over value_vars, beat/backend.py:147,163-165; variable
  * list beat/config.py:83-94 for DCSource + 'duration' of the STF, beat/utility.py:773-797).  Offset -1 = not
- * sampled: value taken from fixed[] in the canonical order [east_shift, north_shift, depth, strike, dip, rake,
- * magnitude, time, duration, hypers..., time_shifts...].                                                    */
+ * sampled: value taken from fixed[] in the canonical order [east_shift[n_sources], north_shift[..], depth, strike,
+ * dip, rake, magnitude, time, duration, hypers..., time_shifts...].                                         */
 typedef struct beatgpu_geom_layout {
     int32_t n_params;
     int32_t off_east_shift, off_north_shift, off_depth;      /* [km] (utility.adjust_point_units converts to m) */
@@ -250,6 +250,9 @@ typedef struct beatgpu_geom_layout {
     int32_t off_hypers, n_hypers;
     int32_t off_time_shifts, n_time_shifts;                  /* hierarchical station corrections [s] (time_shifts_<mapid>,
                                                                 beat/models/seismic.py:198-294); n = 0: none            */
+    int32_t n_sources;                                       /* every source variable is a block of n_sources values
+                                                                (pymc vectors of shape (n_sources,), config.py:1506-1542);
+                                                                their synthetics are stacked (beat/heart.py:3719-3724); 0 = 1 */
 } beatgpu_geom_layout;
 /* event_lat/lon: origin the source's north/east shifts refer to (the reference event, beat/config.py:2045-2066);
  * stf_anchor: HalfSinusoidSTF.anchor, -1 in the reference (beat/config.py:2060).                             */

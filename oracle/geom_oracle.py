@@ -374,29 +374,43 @@ def post_process(wm, t, raw, itmin, chop_bounds=("b", "c")):
 # --------------------------------------------------------------------------------------
 # the composite evaluation
 # --------------------------------------------------------------------------------------
+def point_to_sources(gprob, point):
+    """utility.adjust_point_units (beat/utility.py:651-675: km -> m for the location variables) + utility.split_point
+    (:678-770: one dict per source) + update_source (:773-797; ``duration`` goes to the STF).  ``time`` is relative to
+    the event origin."""
+    n = int(gprob.get("n_sources", 1))
+    out = []
+    for s in range(n):
+        src = {k: float(np.asarray(v).ravel()[s]) for k, v in point.items() if k not in ("hypers", "time_shifts")}
+        for k in ("east_shift", "north_shift", "depth"):
+            src[k] *= KM
+        out.append(src)
+    return out
+
+
 def point_to_source(gprob, point):
-    """utility.adjust_point_units (beat/utility.py:651-675: km -> m for the location variables) + update_source
-    (:773-797; ``duration`` goes to the STF).  ``time`` is relative to the event origin."""
-    src = {k: float(np.asarray(v).ravel()[0]) for k, v in point.items() if k not in ("hypers", "time_shifts")}
-    for k in ("east_shift", "north_shift", "depth"):
-        src[k] *= KM
-    return src
+    """Single-source problems: the one source of ``point_to_sources``."""
+    return point_to_sources(gprob, point)[0]
 
 
 def geometry_synthetics(gprob, point, iw=0):
-    """heart.seis_synthetics(..., outmode='array') for one wavemap and ONE source: [nt, ns] float64."""
+    """heart.seis_synthetics(..., outmode='array') for one wavemap: every source is synthesised and post-processed on
+    its own, then the traces are stacked: [nt, ns] float64."""
     wm = gprob["wavemaps"][iw]
     if wm.get("station_idx") is not None:
         # SeisSynthesizer.perform (beat/pytensorf.py:248-252): arrival_times + time_shifts; the hierarchical is gathered per
         # target with wmap.station_correction_idxs (beat/models/seismic.py:781-784).  Windows, taper and chop follow.
         shifts = np.asarray(point["time_shifts"], dtype=np.float64)[wm["station_idx"]]
         wm = dict(wm, arrival_times=np.asarray(wm["arrival_times"]) + shifts)
-    src = point_to_source(gprob, point)
-    rows = []
-    for t in range(wm["nt"]):
-        raw, itmin = seismogram(gprob, wm, t, src)
-        rows.append(post_process(wm, t, raw, itmin))
-    return np.vstack(rows)
+    outstack = None
+    for src in point_to_sources(gprob, point):                  # engine.process iterates sources, then targets (:3676)
+        rows = []
+        for t in range(wm["nt"]):
+            raw, itmin = seismogram(gprob, wm, t, src)
+            rows.append(post_process(wm, t, raw, itmin))
+        synths = np.vstack(rows)
+        outstack = synths if outstack is None else outstack + synths       # heart.py:3719-3724
+    return outstack
 
 
 def geometry_seismic_eval(gprob, point, return_synth=False):

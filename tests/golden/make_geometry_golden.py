@@ -188,6 +188,8 @@ def main():
                                                    dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)]), chop=("a", "d")),
         # station corrections: SeisSynthesizer.perform hands arrival_times + time_shifts to seis_synthetics (pytensorf.py:248-252)
         dict(name="station_corr", kw=dict(n_stations=3, seed=204, station_corrections=True), chop=("b", "c")),
+        # two sources: seis_synthetics post-processes every (source, target) trace and stacks them (heart.py:3719-3724)
+        dict(name="two_sources", kw=dict(n_stations=2, seed=205, n_sources=2), chop=("b", "c")),
     ]
     for case in cases:
         gprob = S.make_geometry_problem(**case["kw"])
@@ -213,9 +215,9 @@ def main():
             if wm.get("station_idx") is not None:
                 arrival_times = arrival_times + point["time_shifts"][wm["station_idx"]]
             engine = Engine(gprob, dict(wm, arrival_times=arrival_times))
-            src = types.SimpleNamespace(params=O.point_to_source(gprob, point))
+            srcs = [types.SimpleNamespace(params=sp) for sp in O.point_to_sources(gprob, point)]
             synths, tmins = heart.seis_synthetics(
-                engine=engine, sources=[src], targets=targets, arrival_taper=ataper, wavename="any_P", filterer=filterer,
+                engine=engine, sources=srcs, targets=targets, arrival_taper=ataper, wavename="any_P", filterer=filterer,
                 pre_stack_cut=True, arrival_times=arrival_times, outmode="array", chop_bounds=list(case["chop"]))
             synths_ref.append(synths)
             tmins_ref.append(tmins)

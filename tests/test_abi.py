@@ -41,7 +41,7 @@ def test_layout_struct_matches_header():
     # 2 + 3 + 9 int32 fields
     assert ctypes.sizeof(Layout) == 4 * 14
     from beat_b200.lib import GeomLayout
-    assert ctypes.sizeof(GeomLayout) == 4 * 14          # beatgpu_geom_layout: 14 int32 fields
+    assert ctypes.sizeof(GeomLayout) == 4 * 15          # beatgpu_geom_layout: 15 int32 fields
 
 
 def test_no_cpu_fallback_without_device(built_lib):

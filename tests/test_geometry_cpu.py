@@ -196,6 +196,7 @@ GOLDEN_CASES = {
                          filterer=[dict(kind="stepwise", order=2, lower_corner=0.05, upper_corner=0.6),
                                    dict(kind="bandstop", order=2, lower_corner=0.12, upper_corner=0.25)]), ("a", "d")),
     "station_corr": (dict(n_stations=3, seed=204, station_corrections=True), ("b", "c")),
+    "two_sources": (dict(n_stations=2, seed=205, n_sources=2), ("b", "c")),
 }
 
 

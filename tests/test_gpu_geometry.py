@@ -304,7 +304,7 @@ def test_smc_driver_runs_on_the_geometry_engine():
     ev.close()
 
 
-@pytest.mark.parametrize("name", ["stepwise_ml", "bandpass_nn", "bandstop_ad", "station_corr"])
+@pytest.mark.parametrize("name", ["stepwise_ml", "bandpass_nn", "bandstop_ad", "station_corr", "two_sources"])
 def test_cuda_matches_reference_driven_golden(name):
     """CUDA synthetics against tests/golden/geometry_golden.npz -- produced by the reference's own
     heart.seis_synthetics control flow (make_geometry_golden.py); committed fixture, no oracle in the loop."""
@@ -354,3 +354,32 @@ def test_station_corrections():
     _assert_synth_close(synths, ref[2])
     np.testing.assert_allclose(tmins, wm["arrival_times"] + inputs["time_shift"] + wm["taper"][1])
     op.close()
+
+
+def test_two_sources_stack_and_loglike():
+    """Two DC sources per chain (pymc vectors of shape (2,)): synthetics of the sources are stacked (heart.py:3719-3724).
+    The kernels stack the RAW traces and filter once -- equal to the reference's filter-then-stack because demeaning and
+    the IIR filters are linear."""
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=3, n_sources=2, seed=151)
+    assert gprob["n_params"] == 19
+    q0 = S.draw_chains(gprob, 1, seed=1)[0]
+    S.attach_geometry_data(gprob, O.geometry_synthetics(gprob, S.split_point(gprob, q0)))
+    Q = S.draw_chains(gprob, 20, seed=16)
+    Q[0] = q0
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    logpts, _ = ev(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    _assert_synth_close(got, ref)
+    refl = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    _assert_logpts_close(gprob, Q, logpts, refl)
+    # one source switched off (magnitude -> tiny moment) leaves the other source's synthetics
+    Q1 = Q[:4].copy()
+    Q1[:, gprob["offsets"]["magnitude"] + 1] = -20.0
+    g1 = S.make_geometry_problem(n_stations=3, n_sources=1, seed=151)
+    keep = [gprob["offsets"][v] for v, _ in g1["var_order"] if v != "hypers"] + [gprob["offsets"]["hypers"]]
+    ev = _engine(gprob); two = ev.get_synthetics(Q1); ev.close()
+    ev = _engine(g1); one = ev.get_synthetics(np.ascontiguousarray(Q1[:, keep])); ev.close()
+    _assert_synth_close(two, one)
