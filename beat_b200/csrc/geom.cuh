@@ -544,6 +544,13 @@ __global__ void __launch_bounds__(kFilterThreads) __maxnreg__(CAP) trace_filter_
         n_raw_t = a.tgt_nraw[t];
     }
     const int iend = min(n_raw_t, ibeg + ns);                       // nothing after the chop window is needed
+    if (dyn && ibeg + ns > n_raw_t) {
+        // the shifted chop window leaves the computed trace: the reference cannot stack such traces (ValueError,
+        // beat/heart.py:3700-3716); report instead of evaluating on fewer samples
+        if (MODE != 2) a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = CUDART_NAN;
+        else for (int k = 0; k < ns; ++k) a.out[((long)c * a.nt + t) * ns + k] = CUDART_NAN;
+        return;
+    }
     const double mu = a.demean ? a.mean[(long)c * a.nt + t] : 0.0;
     const float4* src = (const float4*)a.rawT + (long)t * a.n4 * a.B + c;
     const double* dat = a.data ? a.data + (long)t * ns : nullptr;

@@ -11,6 +11,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # scipy.signal.butter is called with a one-element list of corners, exactly as pyrocko does; numpy >= 1.25 warns about it
+    config.addinivalue_line("filterwarnings", "ignore:Conversion of an array with ndim > 0 to a scalar:DeprecationWarning")
 
 
 @pytest.fixture(scope="session")
