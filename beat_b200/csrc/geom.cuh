@@ -277,6 +277,8 @@ struct GeomSumArgs {
     const int* tgt_of;                         // target index of each channel of a receiver
     const float* tgt_f;                        // [nt, 3] sensor factors (north, east, down) = (ca*cd, sa*cd, sd) of azimuth/dip
     int slot_floats;                           // floats per shared-memory row slot (multiple of 32)
+    int half_floats;                           // floats per pipeline half: HALF slots + a pad that absorbs the over-reads
+                                               // of the branch-free loops (they must never touch a half that is in flight)
     int n4;                                    // float4 groups per raw trace
     float* rawT;                               // [nt, n4, B, 4] raw traces, chain-interleaved
     double* mean;                              // [B, nt] mean of each raw trace
@@ -289,7 +291,7 @@ struct __align__(16) RowInfo {
     int bytes;                                 // staged bytes (multiple of 16)
     int rel;                                   // record sample of comb index 0:  j = c + rel
     int ja;                                    // first staged record sample
-    int nrec;                                  // samples in the record
+    int jhi;                                   // last staged record sample that the window can address
     float w0, w1;                              // kind 0: weights into north / east; kind 1: w0 into down
     int kind;
     int clamp;                                 // window leaves the record: indices must be clamped (repeat end values)
@@ -300,7 +302,7 @@ struct __align__(16) RowInfo {
 template <int ACC, int HALF>
 __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs a)
 {
-    extern __shared__ __align__(128) float slots[];                               // [2][HALF][slot_floats]
+    extern __shared__ __align__(128) float slots[];                               // [2][half_floats >= HALF * slot_floats]
     float* comb = slots + 4;                                                      // slot 0 is reused once all rows are consumed; 4 zero guard floats in front
     __shared__ RowInfo rows[kGeomMaxRows];
     // candidate table (before compaction) lives at the start of the ring (>= 2304 B for any window): the bulk copies
@@ -339,10 +341,11 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
             valid = !(ri.w0 == 0.f && ri.w1 == 0.f);
             const long rec = (long)node * kGeomNComp + g;
             const int it_rec = a.store.itmin[rec];
-            ri.nrec = a.store.nsamp[rec];
+            const int nrec = a.store.nsamp[rec];
             ri.rel = m0 - it_rec;
-            const int jlo = min(max(ri.rel, 0), ri.nrec - 1), jhi = min(max(ri.rel + ncomb - 1, 0), ri.nrec - 1);
-            ri.clamp = (ri.rel < 0 || ri.rel + ncomb - 1 > ri.nrec - 1) ? 1 : 0;
+            const int jlo = min(max(ri.rel, 0), nrec - 1), jhi = min(max(ri.rel + ncomb - 1, 0), nrec - 1);
+            ri.clamp = (ri.rel < 0 || ri.rel + ncomb - 1 > nrec - 1) ? 1 : 0;
+            ri.jhi = jhi;
             ri.ja = jlo & ~3;
             const int jb = (int)min((long)a.store.ld, (long)((jhi + 4) & ~3));
             ri.bytes = (jb - ri.ja) * 4;
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         for (int i = r0; i < r1; ++i) total += (uint32_t)rows[i].bytes;
         mbar_arrive_expect_tx(&bar[h], total);
         for (int i = r0; i < r1; ++i)
-            tma_load_1d(slots + ((long)h * HALF + (i - r0)) * a.slot_floats, a.store.traces + rows[i].src,
+            tma_load_1d(slots + (long)h * a.half_floats + (long)(i - r0) * a.slot_floats, a.store.traces + rows[i].src,
                         (uint32_t)rows[i].bytes, &bar[h]);
     };
 
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         const int r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
         for (int i = r0; i < r1; ++i) {
             const RowInfo ri = rows[i];
-            const float* s = slots + (h * HALF + (i - r0)) * a.slot_floats;
+            const float* s = slots + h * a.half_floats + (i - r0) * a.slot_floats;
             if (!ri.clamp) {                                                      // window inside the record: s[c + off]
                 const float* so = s + (ri.rel - ri.ja) + tid;                     // one LDS [R + imm] per element
                 if (ri.kind == 0) {
@@ -410,7 +413,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
                 }
             } else {                                                              // repeat the record's first / last value
                 const float* so = s - ri.ja;
-                const int hi = ri.nrec - 1, j0 = tid + ri.rel;
+                const int hi = ri.jhi, j0 = tid + ri.rel;                         // indices past the window clamp onto its last staged sample
                 if (ri.kind == 0) {
 #pragma unroll
                     for (int u = 0; u < ACC; ++u) {
