@@ -51,10 +51,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
 
 // Bounded wait: returns false after ~max_polls unsuccessful polls (each poll itself blocks for a
 // hardware-defined interval), so a lost copy becomes an error flag instead of a hung GPU.
-__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t max_polls = (1u << 22))
+__device__ __forceinline__ bool mbar_wait_bounded(uint64_t* bar, uint32_t parity, uint32_t max_polls = (1u << 22),
+                                                  uint32_t backoff_ns = 0)
 {
-    for (uint32_t i = 0; i < max_polls; ++i)
+    for (uint32_t i = 0; i < max_polls; ++i) {
         if (mbar_try_wait(bar, parity)) return true;
+        if (backoff_ns) __nanosleep(backoff_ns);
+    }
     return false;
 }
 
