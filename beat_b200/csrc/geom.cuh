@@ -393,10 +393,10 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         if (tid == 0 && nb + 1 < nbatch) { fence_proxy_async(); issue(nb + 1); }  // half (nb+1)&1 was released by the barrier below
         const int h = nb & 1;
         // every thread waits on the barrier itself (measured: one polling warp with nanosleep back-off while the others
-        // sleep in bar.sync is 4 % slower -- the back-off adds latency that the three co-resident CTAs do not hide)
-        ok = mbar_wait_bounded(&bar[h], (uint32_t)(nb >> 1) & 1u, 1u << 20);
-        ok = __syncthreads_and(ok);                                               // uniform: a lost copy must not split the CTA
-        if (!ok) break;
+        // sleep in bar.sync is 4 % slower -- the back-off adds latency that the three co-resident CTAs do not hide).
+        // A wait that times out does not leave the loop (all threads must keep meeting at the barrier below): the CTA
+        // finishes on whatever the slot holds and the failure is reported through a.err.
+        if (!mbar_wait_bounded(&bar[h], (uint32_t)(nb >> 1) & 1u, 1u << 20)) ok = false;
         const int r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
         for (int i = r0; i < r1; ++i) {
             const RowInfo ri = rows[i];
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         }
         __syncthreads();
     }
-    if (!ok) { if (tid == 0) atomicAdd(a.err, 1u); return; }
+    if (__syncthreads_or(!ok)) { if (tid == 0) atomicAdd(a.err, 1u); return; }
 
     // ---- per target channel of this receiver: sensor projection, STF convolution, mean, store
     if (tid < 4) slots[tid] = 0.f;                                                // guard: taps padded with zero amplitude read comb[-1..-3]
