@@ -11,7 +11,7 @@ DEPS = [os.path.join(HERE, "csrc", f) for f in ("beatgpu.cu", "sweep.cuh", "stac
 OUT = os.path.join(HERE, "libbeatgpu.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared", "-diag-suppress", "550"]
+              "-shared", "-diag-suppress", "550", "-Xcompiler", "-pthread"]
 
 
 def find_nvcc():

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "beatgpu.h"
@@ -719,26 +720,66 @@ int beatgpu_upload_gflib(beatgpu_ctx* ctx, int wmap_id, int var, const void* tra
     const int ns = (int)dims[4];
     const size_t rows = (size_t)dims[0] * dims[1] * dims[2] * dims[3];
     const size_t ssz = src_dtype == BEATGPU_F32 ? 4 : 8, dsz = store_dtype == BEATGPU_F32 ? 4 : 8;
-    // stream in chunks of <= 256 MiB of source rows through a device staging buffer, repacking on the device
-    const size_t chunk_rows = std::max<size_t>(1, (256u << 20) / ((size_t)ns * ssz));
-    rc = ensure_tmp(ctx, 0, std::min(rows, chunk_rows) * ns * ssz);
-    if (rc) return rc;
-    for (size_t r0 = 0; r0 < rows; r0 += chunk_rows) {
-        const size_t nr = std::min(chunk_rows, rows - r0);
-        CK(cudaMemcpyAsync(ctx->d_tmp[0], (const char*)traces + r0 * ns * ssz, nr * ns * ssz, cudaMemcpyHostToDevice, ctx->stream));
+    // Stream the (possibly memory-mapped, pageable) source in 64 MiB chunks through two pinned host buffers and two
+    // device staging buffers: host threads copy chunk i+1 into pinned memory while the DMA engine moves chunk i and the
+    // repack kernel (dtype conversion + row padding) of chunk i runs behind it.  A source the caller has already
+    // page-locked (beatgpu_host_register) is copied from directly.
+    const size_t row_bytes = (size_t)ns * ssz;
+    const size_t chunk_rows = std::max<size_t>(1, ((size_t)64 << 20) / row_bytes);
+    const size_t chunk_bytes = std::min(rows, chunk_rows) * row_bytes;
+    if ((rc = ensure_tmp(ctx, 0, chunk_bytes)) || (rc = ensure_tmp(ctx, 1, chunk_bytes))) return rc;
+    cudaPointerAttributes attr;
+    bool src_pinned = cudaPointerGetAttributes(&attr, traces) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    if (getenv("BEATGPU_UPLOAD_DIRECT")) src_pinned = true;       // measurement knob: plain cudaMemcpyAsync from the pageable source
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    auto cleanup = [&]() { for (int b = 0; b < 2; ++b) { if (pin[b]) cudaFreeHost(pin[b]); if (ev[b]) cudaEventDestroy(ev[b]); } };
+    if (!src_pinned) {
+        for (int b = 0; b < 2; ++b) {
+            if (cudaHostAlloc(&pin[b], chunk_bytes, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); cleanup(); pin[0] = pin[1] = nullptr; src_pinned = true; break; }
+        }
+    }
+    for (int b = 0; b < 2; ++b) if (cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming) != cudaSuccess) { cleanup(); return fail(ctx, BEATGPU_E_CUDA, "upload_gflib: cudaEventCreate failed"); }
+    const unsigned n_thr = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    size_t i = 0;
+    for (size_t r0 = 0; r0 < rows; r0 += chunk_rows, ++i) {
+        const int b = (int)(i & 1);
+        const size_t nr = std::min(chunk_rows, rows - r0), nbytes = nr * row_bytes;
+        const char* src = (const char*)traces + r0 * row_bytes;
+        if (i >= 2 && cudaEventSynchronize(ev[b]) != cudaSuccess) { cleanup(); return fail(ctx, BEATGPU_E_CUDA, "upload_gflib: staging buffer wait failed"); }
+        const void* h_src = src;
+        if (pin[b]) {                                              // pageable source: parallel host copy into pinned memory
+            std::vector<std::thread> pool;
+            const size_t slice = (nbytes + n_thr - 1) / n_thr;
+            for (unsigned t = 0; t < n_thr; ++t) {
+                const size_t o = (size_t)t * slice;
+                if (o >= nbytes) break;
+                pool.emplace_back([=]() { memcpy((char*)pin[b] + o, src + o, std::min(slice, nbytes - o)); });
+            }
+            for (auto& th : pool) th.join();
+            h_src = pin[b];
+        }
+        cudaError_t e = cudaMemcpyAsync(ctx->d_tmp[b], h_src, nbytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); cleanup(); return fail(ctx, BEATGPU_E_CUDA, "upload_gflib: H2D copy failed: %s", cudaGetErrorString(e)); }
         char* dst = (char*)dptr + r0 * ld * dsz;
         const int blocks = (int)std::min<size_t>(148 * 16, (nr * ld + 255) / 256);
         if (src_dtype == BEATGPU_F64 && store_dtype == BEATGPU_F32)
-            repack_rows_kernel<double, float><<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->d_tmp[0], (float*)dst, (long)nr, ns, (long)ld);
+            repack_rows_kernel<double, float><<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->d_tmp[b], (float*)dst, (long)nr, ns, (long)ld);
         else if (src_dtype == BEATGPU_F64 && store_dtype == BEATGPU_F64)
-            repack_rows_kernel<double, double><<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->d_tmp[0], (double*)dst, (long)nr, ns, (long)ld);
+            repack_rows_kernel<double, double><<<blocks, 256, 0, ctx->stream>>>((const double*)ctx->d_tmp[b], (double*)dst, (long)nr, ns, (long)ld);
         else if (src_dtype == BEATGPU_F32 && store_dtype == BEATGPU_F32)
-            repack_rows_kernel<float, float><<<blocks, 256, 0, ctx->stream>>>((const float*)ctx->d_tmp[0], (float*)dst, (long)nr, ns, (long)ld);
+            repack_rows_kernel<float, float><<<blocks, 256, 0, ctx->stream>>>((const float*)ctx->d_tmp[b], (float*)dst, (long)nr, ns, (long)ld);
         else
-            repack_rows_kernel<float, double><<<blocks, 256, 0, ctx->stream>>>((const float*)ctx->d_tmp[0], (double*)dst, (long)nr, ns, (long)ld);
-        CKL();
-        CK(cudaStreamSynchronize(ctx->stream));
+            repack_rows_kernel<float, double><<<blocks, 256, 0, ctx->stream>>>((const float*)ctx->d_tmp[b], (double*)dst, (long)nr, ns, (long)ld);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { cleanup(); return fail(ctx, BEATGPU_E_CUDA, "upload_gflib: repack launch failed: %s", cudaGetErrorString(e)); }
+        ctx->n_launches++;
+        cudaEventRecord(ev[b], ctx->stream);
     }
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cleanup();
+    if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ctx, BEATGPU_E_CUDA, "upload_gflib: %s", cudaGetErrorString(e)); }
     return BEATGPU_OK;
 }
 
