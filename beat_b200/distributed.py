@@ -61,6 +61,16 @@ def allgather_chains(local, world=None):
     return out
 
 
+def gather_objects(obj):
+    """List of one small picklable object per rank, on every rank (checkpoint metadata; not on the data path)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
 class ShardedPopulation:
     """The population of one SMC stage, sharded over ranks.
 

@@ -157,16 +157,59 @@ class BatchedMetropolis:
         return q_new, logpts_new, like_new, accept
 
 
+def _checkpoint_path(checkpoint_dir, stage):
+    import os
+    return os.path.join(checkpoint_dir, "stage_%d.npz" % stage)
+
+
+def save_stage(checkpoint_dir, stage, q_all, like_all, logpts_all, beta, betas, acc_hist, rng, mh_states):
+    """Per-stage sampler state (the reference pickles ``sample.params`` per stage, beat/sampler/smc.py:549-557,
+    beat/backend.py:1043-1077): end points of all chains, beta history, host RNG state and per-rank proposal state, so
+    that a run can be resumed at a stage boundary (beat/sampler/base.py:618-661) and continues bit-identically."""
+    import os
+    import pickle
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    tmp = _checkpoint_path(checkpoint_dir, stage) + ".tmp.npz"
+    np.savez(tmp, population=q_all, likelihoods=like_all, logpts=logpts_all, beta=np.float64(beta), betas=np.asarray(betas),
+             acceptance=np.asarray(acc_hist), stage=np.int64(stage),
+             rng_state=np.frombuffer(pickle.dumps(rng.bit_generator.state), dtype=np.uint8),
+             mh_states=np.frombuffer(pickle.dumps(mh_states), dtype=np.uint8))
+    os.replace(tmp, _checkpoint_path(checkpoint_dir, stage))           # atomic: an interrupted write never leaves a half stage
+
+
+def load_last_stage(checkpoint_dir):
+    """Latest complete stage file of ``checkpoint_dir`` as a dict, or None."""
+    import glob
+    import os
+    import pickle
+    import re
+    best = None
+    for f in glob.glob(os.path.join(checkpoint_dir, "stage_*.npz")):
+        m = re.search(r"stage_(\d+)\.npz$", f)
+        if m and (best is None or int(m.group(1)) > best[0]):
+            best = (int(m.group(1)), f)
+    if best is None:
+        return None
+    z = np.load(best[1])
+    out = {k: z[k] for k in ("population", "likelihoods", "logpts", "betas", "acceptance")}
+    out["beta"], out["stage"] = float(z["beta"]), int(z["stage"])
+    out["rng_state"] = pickle.loads(z["rng_state"].tobytes())
+    out["mh_states"] = pickle.loads(z["mh_states"].tobytes())
+    return out
+
+
 def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_variation=1.0, tune_interval=None, seed=0,
                sample_factor_final_stage=1, max_stages=200, initial_population=None, update_weights=None, log=None,
-               on_step=None):
+               on_step=None, checkpoint_dir=None, resume=False):
     """Batched restatement of ``smc_sample``'s stage loop (beat/sampler/smc.py:459-546).
 
     Returns dict(population [n_chains, n_params], likelihoods [n_chains], logpts, betas, n_evals, acceptance).
     ``update_weights(map_point) -> None`` mirrors the ``update`` hook (smc.py:492-503): called with the MAP end
     point after each stage; the caller re-uploads weights (``BatchedFFILogLike.update_weights``) and the end points
     are re-evaluated.  ``on_step(stage, step, q, logpts, like)`` is called after every lock-step Metropolis step with
-    this rank's device tensors -- the hook for a trace backend (``beat_b200.backend.BatchedNumpyChains``)."""
+    this rank's device tensors -- the hook for a trace backend (``beat_b200.backend.BatchedNumpyChains``).
+    ``checkpoint_dir``: rank 0 writes ``stage_<k>.npz`` after every stage; ``resume=True`` continues from the latest one
+    (same results as an uninterrupted run: host and per-rank device RNG states are part of the checkpoint)."""
     import torch
     from . import distributed as D
     device = device if device is not None else torch.device("cpu")
@@ -187,11 +230,28 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         pop = rng.uniform(lower, upper, (n_chains, n_params))
     else:
         pop = np.array(initial_population, dtype=np.float64, copy=True)
-    q = torch.as_tensor(pop[lo:hi], device=device).contiguous()
-    logpts, like = mh.initial_llk(q)
-
-    beta, betas, stage = 0.0, [0.0], 0
-    acc_hist = []
+    ckpt = load_last_stage(checkpoint_dir) if (resume and checkpoint_dir) else None
+    if ckpt is not None:
+        if ckpt["population"].shape != (n_chains, n_params):
+            raise ValueError("checkpoint holds a %s population, run expects %s" % (ckpt["population"].shape, (n_chains, n_params)))
+        q = torch.as_tensor(ckpt["population"][lo:hi], device=device).contiguous()
+        like = torch.as_tensor(ckpt["likelihoods"][lo:hi], device=device).contiguous()
+        logpts = torch.as_tensor(ckpt["logpts"][lo:hi], device=device).contiguous()
+        beta, betas, stage = ckpt["beta"], list(ckpt["betas"]), ckpt["stage"]
+        acc_hist = list(ckpt["acceptance"])
+        rng.bit_generator.state = ckpt["rng_state"]
+        st = ckpt["mh_states"][rank] if rank < len(ckpt["mh_states"]) else None
+        if st is not None:
+            mh.scaling = torch.as_tensor(st["scaling"], device=device)
+            mh.gen.set_state(torch.as_tensor(st["gen"], dtype=torch.uint8))
+            mh._n_evals += st["n_evals"]
+        if log:
+            log("resumed after stage %d (beta %.6f)" % (stage, beta))
+    else:
+        q = torch.as_tensor(pop[lo:hi], device=device).contiguous()
+        logpts, like = mh.initial_llk(q)
+        beta, betas, stage = 0.0, [0.0], 0
+        acc_hist = []
     while beta < 1.0 and stage < max_stages:
         like_all = D.allgather_chains(like).cpu().numpy()                    # THE per-stage exchange
         q_all = D.allgather_chains(q).cpu().numpy()
@@ -230,6 +290,12 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         stage += 1
         if log:
             log("stage %d beta %.6f acceptance %.3f" % (stage, beta, acc_hist[-1]))
+        if checkpoint_dir:
+            mine = dict(scaling=mh.scaling.cpu().numpy(), gen=mh.gen.get_state().cpu().numpy(), n_evals=mh.n_evals)
+            states = D.gather_objects(mine)
+            ck_like, ck_q, ck_lp = (D.allgather_chains(x).cpu().numpy() for x in (like, q, logpts))
+            if rank == 0:
+                save_stage(checkpoint_dir, stage, ck_q, ck_like, ck_lp, beta, betas, acc_hist, rng, states)
     like_all = D.allgather_chains(like).cpu().numpy()
     q_all = D.allgather_chains(q).cpu().numpy()
     logpts_all = D.allgather_chains(logpts).cpu().numpy()
