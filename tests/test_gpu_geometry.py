@@ -383,3 +383,47 @@ def test_two_sources_stack_and_loglike():
     ev = _engine(gprob); two = ev.get_synthetics(Q1); ev.close()
     ev = _engine(g1); one = ev.get_synthetics(np.ascontiguousarray(Q1[:, keep])); ev.close()
     _assert_synth_close(two, one)
+
+
+def test_two_wavemaps_p_and_s_windows():
+    """Two wavemaps in one problem (the reference loops over self.wavemaps, beat/models/seismic.py:779-829, and
+    concatenates their logpts, :837): a P window and a longer S window with its own filter, hyperparameter and sample
+    count share the store and the chain parameters."""
+    import copy
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=2, seed=161)
+    wm_p = gprob["wavemaps"][0]
+    wm_s = copy.deepcopy(wm_p)
+    vp, vs = gprob["store"]["vp"], gprob["store"]["vs"]
+    wm_s["arrival_times"] = np.rint(wm_p["arrival_times"] * vp / vs / 0.5) * 0.5          # S arrives later; snapped to the grid
+    wm_s["taper"] = (-6.0, -4.0, 26.0, 28.0)
+    wm_s["ns"] = 60
+    wm_s["nsamples"] = np.full(wm_s["nt"], 60, dtype=np.int32)
+    wm_s["filterer"] = [dict(kind="bandpass", order=2, lower_corner=0.03, upper_corner=0.3)]
+    wm_s["interpolation"] = "nearest_neighbor"
+    gprob["wavemaps"].append(wm_s)
+    # a second hyperparameter for the S wavemap
+    gprob["n_hypers"] = 2
+    gprob["var_order"] = [(v, n) if v != "hypers" else (v, 2) for v, n in gprob["var_order"]]
+    gprob["n_params"] += 1
+    gprob["priors"]["hypers"] = (np.zeros(2), np.full(2, 4.0))
+    wm_s["hyper_idx"] = np.ones(wm_s["nt"], dtype=np.int32)
+    q0 = S.draw_chains(gprob, 1, seed=1)[0]
+    for iw in range(2):
+        S.attach_geometry_data(gprob, O.geometry_synthetics(gprob, S.split_point(gprob, q0), iw), iw=iw, seed=5 + iw)
+    Q = S.draw_chains(gprob, 16, seed=17)
+    Q[0] = q0
+    ev = _engine(gprob)
+    assert ev.n_out == 12
+    logpts, like = ev(Q)
+    syn_s = ev.get_synthetics(Q, wmap_index=1)
+    ev.close()
+    ref = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    assert ref.shape == (16, 12)
+    for iw, sl in enumerate((slice(0, 6), slice(6, 12))):
+        wm = gprob["wavemaps"][iw]
+        h = Q[:, gprob["offsets"]["hypers"] + iw][:, None]
+        const = wm["slog_pdet"][None, :] + wm["nsamples"][None, :] * (2.0 * h + np.log(2.0 * np.pi))
+        np.testing.assert_allclose(-2.0 * logpts[:, sl] - const, -2.0 * ref[:, sl] - const, rtol=1e-5)
+    np.testing.assert_allclose(like, ref.sum(axis=1), rtol=1e-5)
+    _assert_synth_close(syn_s, np.array([O.geometry_synthetics(gprob, p, 1) for p in _points(gprob, Q)]))
