@@ -303,7 +303,6 @@ template <int ACC, int HALF>
 __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs a)
 {
     extern __shared__ __align__(128) float slots[];                               // [2][half_floats >= HALF * slot_floats]
-    float* comb = slots + 4;                                                      // slot 0 is reused once all rows are consumed; 4 zero guard floats in front
     __shared__ RowInfo rows[kGeomMaxRows];
     // candidate table (before compaction) lives at the start of the ring (>= 2304 B for any window): the bulk copies
     // that overwrite it are issued by thread 0 behind a fence.proxy.async after the compaction has been barriered
@@ -432,9 +431,16 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     }
     if (__syncthreads_or(!ok)) { if (tid == 0) atomicAdd(a.err, 1u); return; }
 
-    // ---- per target channel of this receiver: sensor projection, STF convolution, mean, store
-    if (tid < 4) slots[tid] = 0.f;                                                // guard: taps padded with zero amplitude read comb[-1..-3]
+    // ---- per target channel of this receiver: sensor projection, STF convolution, mean, store.
+    // The combined trace is laid out in slot 0 so that comb[n_stf - 1] is 16-byte aligned: a thread then produces four
+    // consecutive output samples from aligned LDS.128 windows (raw[i] = sum_k amp[k] comb[i + n_stf-1 - k]; per 4 taps
+    // 3 vector loads + 16 FMA) and writes them as one float4 into the chain-interleaved raw layout.  Zero guards in front
+    // of and behind the trace stand in for the taps / samples that padding to multiples of four adds.
+    const int padc = (4 - ((n_stf - 1) & 3)) & 3;
+    float* comb = slots + 8 + padc;
+    if (tid < 8 + padc) slots[tid] = 0.f;
     const int n_tap4 = (n_stf + 3) >> 2;
+    const int nq = (n_raw + 3) >> 2;
     for (int q = a.rcv_first[r]; q < a.rcv_first[r + 1]; ++q) {
         const int t = a.tgt_of[q];
         const float fn = a.tgt_f[3 * t], fe = a.tgt_f[3 * t + 1], fd = a.tgt_f[3 * t + 2];
@@ -443,25 +449,30 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
             const int cc = tid + u * kGeomThreads;
             if (cc < ncomb) comb[cc] = fn * acc_n[u] + fe * acc_e[u] + fd * acc_d[u];
         }
+        if (tid < 4) comb[ncomb + tid] = 0.f;
         __syncthreads();
         double lsum = 0.0;
-        float* dst = a.rawT + (((long)t * a.n4 + (tid >> 2)) * a.B + c) * 4 + (tid & 3);     // sample i = tid + 256 m
-        const long dstep = (long)(kGeomThreads / 4) * a.B * 4;
-        const float* cw = comb + (n_stf - 1) + tid;
-        for (int i = tid; i < n_raw; i += kGeomThreads, dst += dstep, cw += kGeomThreads) {
-            float v0 = 0.f, v1 = 0.f;                                             // raw[i] = sum_k amp[k] comb[i + n_stf-1 - k], four taps per step
-            for (int k4 = 0; k4 < n_tap4; ++k4) {
-                const float4 am = *(const float4*)(s_amp + 4 * k4);
-                const float* cp4 = cw - 4 * k4;
-                v0 = fmaf(am.x, cp4[0], v0);
-                v1 = fmaf(am.y, cp4[-1], v1);
-                v0 = fmaf(am.z, cp4[-2], v0);
-                v1 = fmaf(am.w, cp4[-3], v1);
+        float4* dst = (float4*)a.rawT + ((long)t * a.n4 + tid) * a.B + c;                     // quad i4 = tid + 256 m
+        const long dstep = (long)kGeomThreads * a.B;
+        const float* wb = comb + (n_stf - 1) + 4 * tid;                                       // 16-byte aligned
+        for (int i4 = tid; i4 < nq; i4 += kGeomThreads, dst += dstep, wb += 4 * kGeomThreads) {
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+            for (int c4 = 0; c4 < n_tap4; ++c4) {
+                const float4 am = *(const float4*)(s_amp + 4 * c4);
+                const float4 lo = *(const float4*)(wb - 4 * c4 - 4);                          // comb offsets -4 .. -1
+                const float4 hi = *(const float4*)(wb - 4 * c4);                              //               0 ..  3
+                v0 = fmaf(am.x, hi.x, v0); v0 = fmaf(am.y, lo.w, v0); v0 = fmaf(am.z, lo.z, v0); v0 = fmaf(am.w, lo.y, v0);
+                v1 = fmaf(am.x, hi.y, v1); v1 = fmaf(am.y, hi.x, v1); v1 = fmaf(am.z, lo.w, v1); v1 = fmaf(am.w, lo.z, v1);
+                v2 = fmaf(am.x, hi.z, v2); v2 = fmaf(am.y, hi.y, v2); v2 = fmaf(am.z, hi.x, v2); v2 = fmaf(am.w, lo.w, v2);
+                v3 = fmaf(am.x, hi.w, v3); v3 = fmaf(am.y, hi.z, v3); v3 = fmaf(am.z, hi.y, v3); v3 = fmaf(am.w, hi.x, v3);
             }
-            float v = v0 + v1;
-            if (a.accumulate) v += *dst;
-            *dst = v;
-            lsum += (double)v;
+            if (a.accumulate) { const float4 p = *dst; v0 += p.x; v1 += p.y; v2 += p.z; v3 += p.w; }
+            *dst = make_float4(v0, v1, v2, v3);
+            const int i = 4 * i4;                                                             // the last quad may be partial
+            lsum += (double)v0;
+            if (i + 1 < n_raw) lsum += (double)v1;
+            if (i + 2 < n_raw) lsum += (double)v2;
+            if (i + 3 < n_raw) lsum += (double)v3;
         }
         for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
         if ((tid & 31) == 0) red[tid >> 5] = lsum;
