@@ -39,6 +39,7 @@ constexpr int kGeomMaxNodes = 4;               // multilinear vicinity in (sourc
 constexpr int kGeomMaxRows = kGeomMaxNodes * kGeomNComp;
 constexpr int kGeomMaxStf = 64;                // STF points on the time grid (duration <= 63 * deltat)
 constexpr int kGeomThreads = 256;
+constexpr int kGeomMaxHalfRows = 4;            // rows per pipeline half: template parameter HALF (3 or 4)
 constexpr int kGeomMaxSec = 3;                 // IIR sections in cascade
 constexpr int kGeomMaxOrder = 8;
 
@@ -276,6 +277,8 @@ struct GeomSumArgs {
     const int* tgt_of;                         // target index of each channel of a receiver
     const float* tgt_f;                        // [nt, 3] sensor factors (north, east, down) = (ca*cd, sa*cd, sd) of azimuth/dip
     int slot_floats;                           // floats per shared-memory row slot (multiple of 32)
+    int half_floats;                           // floats per pipeline half: HALF slots + a pad that absorbs the over-reads
+                                               // of the branch-free loops (they must never touch a half that is in flight)
     int n4;                                    // float4 groups per raw trace
     float* rawT;                               // [nt, n4, B, 4] raw traces, chain-interleaved
     double* mean;                              // [B, nt] mean of each raw trace
@@ -294,20 +297,18 @@ struct __align__(16) RowInfo {
     int clamp;                                 // window leaves the record: indices must be clamped (repeat end values)
 };
 
-// NS row slots of ~9 KB at config-2 size form a ring with a full / empty mbarrier pair per slot (NS = 6: 54 KB, four CTAs
-// per SM; NS = 8: 72 KB, three; BEATGPU_GEOM_HALF = 3 | 4 selects NS = 2 x that; measurements in profiles/README.md).
-// Thread 0 keeps NS - 1 rows in flight: it re-arms a slot as soon as all 256 threads have arrived on its empty barrier,
-// so there is no CTA-wide barrier inside the row loop and the threads may drift apart by up to NS - 1 rows.
-template <int ACC, int NS>
-__global__ void __launch_bounds__(kGeomThreads, NS <= 6 ? 4 : 3) gf_delay_sum_kernel(GeomSumArgs a)
+// HALF rows per pipeline half: 2*HALF slots of ~9 KB at config-2 size -> HALF = 4: 72 KB, three CTAs per SM;
+// HALF = 3: 54 KB, four CTAs per SM (BEATGPU_GEOM_HALF selects; measurements in profiles/README.md).
+template <int ACC, int HALF>
+__global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs a)
 {
-    extern __shared__ __align__(128) float slots[];                               // [NS][slot_floats]
+    extern __shared__ __align__(128) float slots[];                               // [2][half_floats >= HALF * slot_floats]
     __shared__ RowInfo rows[kGeomMaxRows];
     // candidate table (before compaction) lives at the start of the ring (>= 2304 B for any window): the bulk copies
     // that overwrite it are issued by thread 0 behind a fence.proxy.async after the compaction has been barriered
     RowInfo* cand = reinterpret_cast<RowInfo*>(slots);
     __shared__ unsigned char s_valid[kGeomMaxRows];
-    __shared__ __align__(8) uint64_t full[NS], empty[NS];
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ __align__(16) float s_amp[kGeomMaxStf + 4];                        // zero padded to a multiple of 4 taps
     __shared__ double red[kGeomThreads / 32];
     __shared__ int s_nrows;
@@ -353,7 +354,8 @@ __global__ void __launch_bounds__(kGeomThreads, NS <= 6 ? 4 : 3) gf_delay_sum_ke
         s_valid[tid] = valid ? 1 : 0;
     }
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kGeomThreads); }
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -365,47 +367,50 @@ __global__ void __launch_bounds__(kGeomThreads, NS <= 6 ? 4 : 3) gf_delay_sum_ke
     }
     __syncthreads();
     const int nrows = s_nrows;
+    const int nbatch = (nrows + HALF - 1) / HALF;
 
-    // Accumulator u of a thread belongs to comb index tid + 256 u.  The accumulate loops are branch-free; (ACC - 2) * 256
-    // <= n_raw always holds, so only the last two accumulators can lie past the window: their index is clamped onto
-    // its last sample (they are never read) and no load ever leaves the staged part of a slot.
+    // Accumulator u of a thread belongs to comb index tid + 256 u.  The loops below are branch-free: indices past the
+    // window (>= ncomb) read whatever lies behind it in shared memory (the ring is padded so that this stays in
+    // bounds) and those accumulators are never read.
     float acc_n[ACC], acc_e[ACC], acc_d[ACC];
 #pragma unroll
     for (int u = 0; u < ACC; ++u) acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
-    const int lastc = ncomb - 1;
-    bool ok = true;
 
-    auto issue = [&](int row) {                                                   // thread 0 only: stage `row` in slot row % NS
-        const int sl = row % NS;
-        if (row >= NS && !mbar_wait_bounded(&empty[sl], (uint32_t)(row / NS - 1) & 1u, 1u << 20)) ok = false;
-        fence_proxy_async();                                                      // generic reads of the slot -> async write
-        mbar_arrive_expect_tx(&full[sl], (uint32_t)rows[row].bytes);
-        tma_load_1d(slots + (long)sl * a.slot_floats, a.store.traces + rows[row].src, (uint32_t)rows[row].bytes, &full[sl]);
+    auto issue = [&](int nb) {                                                    // thread 0 only
+        const int h = nb & 1, r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
+        uint32_t total = 0;
+        for (int i = r0; i < r1; ++i) total += (uint32_t)rows[i].bytes;
+        mbar_arrive_expect_tx(&bar[h], total);
+        for (int i = r0; i < r1; ++i)
+            tma_load_1d(slots + (long)h * a.half_floats + (long)(i - r0) * a.slot_floats, a.store.traces + rows[i].src,
+                        (uint32_t)rows[i].bytes, &bar[h]);
     };
 
-    if (tid == 0)
-        for (int row = 0; row < min(nrows, NS - 1); ++row) issue(row);
-    for (int i = 0; i < nrows; ++i) {
-        if (tid == 0 && i + NS - 1 < nrows) issue(i + NS - 1);                    // refills the slot released in iteration i - 1
-        const int sl = i % NS;
-        // a wait that times out does not leave the loop: the CTA finishes on whatever the slot holds and reports via a.err
-        if (!mbar_wait_bounded(&full[sl], (uint32_t)(i / NS) & 1u, 1u << 20)) ok = false;
-        {
+    if (tid == 0 && nbatch > 0) { fence_proxy_async(); issue(0); }
+    bool ok = true;
+    for (int nb = 0; nb < nbatch; ++nb) {
+        if (tid == 0 && nb + 1 < nbatch) { fence_proxy_async(); issue(nb + 1); }  // half (nb+1)&1 was released by the barrier below
+        const int h = nb & 1;
+        // every thread waits on the barrier itself (measured: one polling warp with nanosleep back-off while the others
+        // sleep in bar.sync is 4 % slower -- the back-off adds latency that the three co-resident CTAs do not hide).
+        // A wait that times out does not leave the loop (all threads must keep meeting at the barrier below): the CTA
+        // finishes on whatever the slot holds and the failure is reported through a.err.
+        if (!mbar_wait_bounded(&bar[h], (uint32_t)(nb >> 1) & 1u, 1u << 20)) ok = false;
+        const int r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
+        for (int i = r0; i < r1; ++i) {
             const RowInfo ri = rows[i];
-            const float* s = slots + sl * a.slot_floats;
+            const float* s = slots + h * a.half_floats + (i - r0) * a.slot_floats;
             if (!ri.clamp) {                                                      // window inside the record: s[c + off]
-                const float* so0 = s + (ri.rel - ri.ja);
-                const float* so = so0 + tid;                                      // one LDS [R + imm] per element
+                const float* so = s + (ri.rel - ri.ja) + tid;                     // one LDS [R + imm] per element
                 if (ri.kind == 0) {
 #pragma unroll
                     for (int u = 0; u < ACC; ++u) {
-                        const float x = (u < ACC - 2) ? so[u * kGeomThreads] : so0[min(tid + u * kGeomThreads, lastc)];
+                        const float x = so[u * kGeomThreads];
                         acc_n[u] = fmaf(ri.w0, x, acc_n[u]); acc_e[u] = fmaf(ri.w1, x, acc_e[u]);
                     }
                 } else {
 #pragma unroll
-                    for (int u = 0; u < ACC; ++u)
-                        acc_d[u] = fmaf(ri.w0, (u < ACC - 2) ? so[u * kGeomThreads] : so0[min(tid + u * kGeomThreads, lastc)], acc_d[u]);
+                    for (int u = 0; u < ACC; ++u) acc_d[u] = fmaf(ri.w0, so[u * kGeomThreads], acc_d[u]);
                 }
             } else {                                                              // repeat the record's first / last value
                 const float* so = s - ri.ja;
@@ -422,7 +427,7 @@ __global__ void __launch_bounds__(kGeomThreads, NS <= 6 ? 4 : 3) gf_delay_sum_ke
                 }
             }
         }
-        mbar_arrive(&empty[sl]);                                                  // this thread is done with the slot
+        __syncthreads();
     }
     if (__syncthreads_or(!ok)) { if (tid == 0) atomicAdd(a.err, 1u); return; }
 
