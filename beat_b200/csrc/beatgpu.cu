@@ -500,7 +500,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_STACK_MODE")) c->stack_mode = (strcmp(e, "fused") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_GEO_MODE")) c->geo_mode = (strcmp(e, "simple") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_FILTER_CAP")) { int v = atoi(e); if (v == 80 || v == 0) c->filter_cap = v; }
-    if (const char* e = getenv("BEATGPU_GEOM_HALF")) { int v = atoi(e); if (v == 3 || v == 4) c->geom_half = v; }
+    if (const char* e = getenv("BEATGPU_GEOM_HALF")) { int v = atoi(e); if (v >= 2 && v <= 4) c->geom_half = v; }
     if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) c->chunk_patches = v; }
     *out = c;
     return BEATGPU_OK;

@@ -276,7 +276,7 @@ struct GeomSumArgs {
     const int* rcv_first;                      // [nr + 1] CSR into tgt_of
     const int* tgt_of;                         // target index of each channel of a receiver
     const float* tgt_f;                        // [nt, 3] sensor factors (north, east, down) = (ca*cd, sa*cd, sd) of azimuth/dip
-    int slot_floats;                           // floats per shared-memory row slot (multiple of 32)
+    int slot_floats;                           // floats per shared-memory row slot (multiple of 4)
     int half_floats;                           // floats per pipeline half: HALF slots + a pad that absorbs the over-reads
                                                // of the branch-free loops (they must never touch a half that is in flight)
     int n4;                                    // float4 groups per raw trace
@@ -299,16 +299,17 @@ struct __align__(16) RowInfo {
 
 // HALF rows per pipeline half: 2*HALF slots of ~9 KB at config-2 size -> HALF = 4: 72 KB, three CTAs per SM;
 // HALF = 3: 54 KB, four CTAs per SM (BEATGPU_GEOM_HALF selects; measurements in profiles/README.md).
-template <int ACC, int HALF>
+// NST pipeline stages of HALF rows each (NST = 2: double buffering; NST = 3 keeps two batches in flight).
+template <int ACC, int HALF, int NST>
 __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs a)
 {
-    extern __shared__ __align__(128) float slots[];                               // [2][half_floats >= HALF * slot_floats]
+    extern __shared__ __align__(128) float slots[];                               // [NST][half_floats >= HALF * slot_floats]
     __shared__ RowInfo rows[kGeomMaxRows];
     // candidate table (before compaction) lives at the start of the ring (>= 2304 B for any window): the bulk copies
     // that overwrite it are issued by thread 0 behind a fence.proxy.async after the compaction has been barriered
     RowInfo* cand = reinterpret_cast<RowInfo*>(slots);
     __shared__ unsigned char s_valid[kGeomMaxRows];
-    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ __align__(8) uint64_t bar[NST];
     __shared__ __align__(16) float s_amp[kGeomMaxStf + 4];                        // zero padded to a multiple of 4 taps
     __shared__ double red[kGeomThreads / 32];
     __shared__ int s_nrows;
@@ -354,8 +355,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         s_valid[tid] = valid ? 1 : 0;
     }
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        for (int i = 0; i < NST; ++i) mbar_init(&bar[i], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -377,7 +377,7 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
     for (int u = 0; u < ACC; ++u) acc_n[u] = acc_e[u] = acc_d[u] = 0.f;
 
     auto issue = [&](int nb) {                                                    // thread 0 only
-        const int h = nb & 1, r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
+        const int h = nb % NST, r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
         uint32_t total = 0;
         for (int i = r0; i < r1; ++i) total += (uint32_t)rows[i].bytes;
         mbar_arrive_expect_tx(&bar[h], total);
@@ -386,16 +386,20 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
                         (uint32_t)rows[i].bytes, &bar[h]);
     };
 
-    if (tid == 0 && nbatch > 0) { fence_proxy_async(); issue(0); }
+    if (tid == 0) {
+        fence_proxy_async();
+        for (int nb = 0; nb < min(nbatch, NST - 1); ++nb) issue(nb);
+    }
     bool ok = true;
     for (int nb = 0; nb < nbatch; ++nb) {
-        if (tid == 0 && nb + 1 < nbatch) { fence_proxy_async(); issue(nb + 1); }  // half (nb+1)&1 was released by the barrier below
-        const int h = nb & 1;
+        // stage (nb + NST - 1) % NST == (nb - 1) % NST was released by the barrier that ended iteration nb - 1
+        if (tid == 0 && nb + NST - 1 < nbatch) { fence_proxy_async(); issue(nb + NST - 1); }
+        const int h = nb % NST;
         // every thread waits on the barrier itself (measured: one polling warp with nanosleep back-off while the others
         // sleep in bar.sync is 4 % slower -- the back-off adds latency that the three co-resident CTAs do not hide).
         // A wait that times out does not leave the loop (all threads must keep meeting at the barrier below): the CTA
         // finishes on whatever the slot holds and the failure is reported through a.err.
-        if (!mbar_wait_bounded(&bar[h], (uint32_t)(nb >> 1) & 1u, 1u << 20)) ok = false;
+        if (!mbar_wait_bounded(&bar[h], (uint32_t)(nb / NST) & 1u, 1u << 20)) ok = false;
         const int r0 = nb * HALF, r1 = min(nrows, r0 + HALF);
         for (int i = r0; i < r1; ++i) {
             const RowInfo ri = rows[i];
