@@ -255,12 +255,27 @@ def run_reference_arm(args):
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML (pynvml) is polled every few milliseconds
+    from a thread that is already running when the region starts -- a freshly spawned `nvidia-smi -lms` often delivers its
+    first line only after a 120 ms region has ended; it remains the fall-back when pynvml is missing."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self._stop = [], None, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -270,11 +285,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), sm, mask))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
     def stop(self, t0, t1):
+        if self.nvml:
+            self._stop = True
+            self.thread.join(timeout=1.0)
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            reasons = sorted({name for _, _, mask in inside for bit, name in self.NVML_REASONS if mask & bit})
+            return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": self.max_sm,
+                    "reasons": reasons, "samples": len(inside), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -294,7 +330,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
@@ -393,10 +429,10 @@ def _run_gpu_arm(args):
 
     log("first evaluation ok (stack kernel %.2f ms); timing" % ev.ctx.last_stack_ms())
     # ---------------- value: inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None       # polling before the warm-up: samples exist from step 0
     for i in range(args.warmup):
         step_resident(i)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = ev.ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stack_ms = []
@@ -617,6 +653,7 @@ def run_c2(args):
     q_dev = [torch.from_numpy(q).to(dev) for q in Qs]
     lp = torch.empty((B, ev.n_out), dtype=torch.float64, device=dev)
     lk = torch.empty((B,), dtype=torch.float64, device=dev)
+    sampler = ClockSampler(0)
     for i in range(args.warmup):
         ev.eval_device(q_dev[i % 4], lp, lk)
     torch.cuda.synchronize()
@@ -624,11 +661,13 @@ def run_c2(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sum_ms = []
     launches0 = ev.ctx.launch_count()
+    t_wall0 = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         ev.eval_device(q_dev[i % 4], lp, lk)
     e1.record()
     torch.cuda.synchronize()
+    clocks = sampler.stop(t_wall0, time.perf_counter())
     launches = ev.ctx.launch_count() - launches0
     ms = e0.elapsed_time(e1) / args.steps
     for i in range(args.steps):                                # kernel time of the delay-and-sum, one step at a time
@@ -659,7 +698,7 @@ def run_c2(args):
                        "chains_per_gpu": B, "gf_store_MB": gprob["store"]["traces"].nbytes / 1e6,
                        "l2": "q rotates between steps; raw-trace scratch %.1f GB > L2" % (B * wm["nt"] * 2200 * 4 / 1e9)},
             "e2e": {"value": B / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(Qs[0].nbytes), "d2h_bytes_per_step": int(lp_pin.numel() * 8 + lk_pin.numel() * 8)},
-            "gpu_launches": int(launches), "all_finite": finite, "index_violations_warmup": int(viol),
+            "gpu_launches": int(launches), "all_finite": finite, "index_violations_warmup": int(viol), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "geom_plan_kernel+gf_delay_sum_kernel", "achieved": alg / (k_ms / 1e3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / (k_ms / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
                          "peak_source": peaks["source"], "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
