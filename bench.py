@@ -271,6 +271,10 @@ class ClockSampler:
             self.nvml = pynvml
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.handle) / 1000.0
+            except Exception:
+                self.power_limit = None
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return
@@ -294,7 +298,11 @@ class ClockSampler:
                     mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
                 except Exception:
                     mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                self.rows.append((time.perf_counter(), sm, mask))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = None
+                self.rows.append((time.perf_counter(), sm, mask, pw))
             except Exception:
                 pass
             time.sleep(0.004)
@@ -308,9 +316,13 @@ class ClockSampler:
             self._stop = True
             self.thread.join(timeout=1.0)
             inside = [r for r in self.rows if t0 <= r[0] <= t1]
-            reasons = sorted({name for _, _, mask in inside for bit, name in self.NVML_REASONS if mask & bit})
+            reasons = sorted({name for r in inside for bit, name in self.NVML_REASONS if r[2] & bit})
+            pw = [r[3] for r in inside if r[3] is not None]
             return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": self.max_sm,
-                    "reasons": reasons, "samples": len(inside), "source": "nvml"}
+                    "reasons": reasons, "samples": len(inside), "source": "nvml",
+                    # the board runs at its power limit under this kernel: clocks a few percent below max are power
+                    # management, whether or not NVML flags sw_power_cap at the sampling instants
+                    "power_w": float(np.median(pw)) if pw else None, "power_limit_w": self.power_limit}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
