@@ -320,8 +320,7 @@ class ClockSampler:
             pw = [r[3] for r in inside if r[3] is not None]
             return {"sm_mhz": float(np.median([r[1] for r in inside])) if inside else None, "sm_max_mhz": self.max_sm,
                     "reasons": reasons, "samples": len(inside), "source": "nvml",
-                    # the board runs at its power limit under this kernel: clocks a few percent below max are power
-                    # management, whether or not NVML flags sw_power_cap at the sampling instants
+                    # NVML's power figure is a ~1 s moving average, so it lags a 0.1 s region; reported for context
                     "power_w": float(np.median(pw)) if pw else None, "power_limit_w": self.power_limit}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
