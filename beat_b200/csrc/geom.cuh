@@ -16,15 +16,19 @@
 //                            discretises the chain's source time function onto the store's time grid.
 //   gf_delay_sum_kernel      CTA per (receiver, chain) -- THE BYTE MOVER.  The <= 4 nodes x 10 components GF traces the
 //                            plan selected are windowed and staged in shared memory by the TMA engine
-//                            (cp.async.bulk, two half-rings of 5 rows, one mbarrier each); 256 threads accumulate the
-//                            north / east / down seismograms in f32 registers (the store's dtype, as pyrocko does), then
-//                            per target channel: sensor projection, convolution with the STF amplitudes, trace mean,
-//                            raw trace to HBM in a chain-interleaved layout.  The 3 channels of a station share one
-//                            pass over the rows.  Receiver-major grid: concurrent CTAs read the same few store nodes.
+//                            (cp.async.bulk; two pipeline stages of 3 rows, one mbarrier + one CTA barrier per batch);
+//                            256 threads accumulate the north / east / down seismograms in f32 registers (the store's
+//                            dtype, as pyrocko does) with branch-free loops, then per target channel: sensor
+//                            projection, convolution with the STF amplitudes on aligned LDS.128 windows, trace mean,
+//                            raw trace to HBM as float4 in a chain-interleaved layout.  The 3 channels of a station
+//                            share one pass over the rows.  Receiver-major grid: concurrent CTAs read the same few
+//                            store nodes out of L2.
 //   trace_filter_misfit_kernel  thread per (target, chain): streams its raw trace (coalesced float4 across chains)
 //                            through the IIR cascade in f64 (scipy.signal.lfilter's direct form II transposed), taper,
 //                            chop, residual against the data and -- for diagonal / narrow-band weights -- the
 //                            covariance-weighted misfit and logpt, without the synthetic ever being written.
+// Several sources per chain are stacked by running plan + delay-and-sum once per source (the second pass adds to the
+// raw traces); station corrections move the window, the chop and the taper with the chain's time shift.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
