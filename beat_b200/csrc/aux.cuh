@@ -138,4 +138,68 @@ __global__ void sum_like_kernel(const double* __restrict__ logpts, double* __res
     like[c] = s;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Weight matrices that are already on the device (per-stage covariance update, beat/models/seismic.py:1509-1534):
+// structure detection and repacking into the layouts the misfit kernels read, without a host round trip.
+//   pass 1: max |U_t| per target;  pass 2: any entry below the diagonal above the threshold? largest super-diagonal
+//   offset above the threshold?  (same rules as the host path of beatgpu_update_weights)
+__global__ void weights_absmax_kernel(const double* __restrict__ U, int ns, double* __restrict__ amax, int* __restrict__ has_nan)
+{
+    __shared__ double red[32];
+    const int t = blockIdx.x;
+    const double* Ut = U + (long)t * ns * ns;
+    double m = 0.0;
+    bool nan = false;
+    for (long i = threadIdx.x; i < (long)ns * ns; i += blockDim.x) {
+        const double v = fabs(Ut[i]);
+        if (!(v == v)) nan = true;
+        m = fmax(m, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    if (nan) atomicExch(has_nan, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmax(m, red[w]);
+        amax[t] = m;
+    }
+}
+
+__global__ void weights_structure_kernel(const double* __restrict__ U, int ns, const double* __restrict__ amax, double band_rtol,
+                                         int* __restrict__ lower, int* __restrict__ bw)
+{
+    const int t = blockIdx.x;
+    const double* Ut = U + (long)t * ns * ns;
+    const double thr = band_rtol * amax[t];
+    int my_bw = 0, my_lower = 0;
+    for (long e = threadIdx.x; e < (long)ns * ns; e += blockDim.x) {
+        const int i = (int)(e / ns), j = (int)(e % ns);
+        if (fabs(Ut[e]) > thr) {
+            if (j < i) my_lower = 1;
+            else my_bw = max(my_bw, j - i);
+        }
+    }
+    if (my_lower) atomicExch(lower, 1);
+    if (my_bw) atomicMax(bw, my_bw);
+}
+
+// mode 0: diagonal W[t][k] = U[t][k][k]; mode 1: band W[t][j][k] = U[t][k][k+j] (0 past the edge); mode 2: dense transposed
+// W[t][j][k] = U[t][k][j]
+__global__ void weights_repack_kernel(const double* __restrict__ U, double* __restrict__ W, int nt, int ns, int mode, int bw)
+{
+    const long n = mode == 0 ? (long)nt * ns : (mode == 1 ? (long)nt * (bw + 1) * ns : (long)nt * ns * ns);
+    for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        if (mode == 0) {
+            const int t = (int)(e / ns), k = (int)(e % ns);
+            W[e] = U[((long)t * ns + k) * ns + k];
+        } else if (mode == 1) {
+            const int k = (int)(e % ns), j = (int)((e / ns) % (bw + 1)), t = (int)(e / ((long)ns * (bw + 1)));
+            W[e] = (k + j < ns) ? U[((long)t * ns + k) * ns + (k + j)] : 0.0;
+        } else {
+            const int k = (int)(e % ns), j = (int)((e / ns) % ns), t = (int)(e / ((long)ns * ns));
+            W[e] = U[((long)t * ns + k) * ns + j];
+        }
+    }
+}
+
 }  // namespace beatgpu

@@ -852,6 +852,49 @@ int beatgpu_update_weights(beatgpu_ctx* ctx, int wmap_id, const double* U, const
     return BEATGPU_OK;
 }
 
+int beatgpu_update_weights_dev(beatgpu_ctx* ctx, int wmap_id, const double* U_dev, const double* slog_pdet_dev, double band_rtol)
+{
+    GET_WMAP(wmap_id);
+    if (!U_dev || !slog_pdet_dev) return fail(ctx, BEATGPU_E_ARG, "update_weights_dev: NULL");
+    if (band_rtol < 0) band_rtol = 1e-13;
+    const int nt = w.nt, ns = w.ns;
+    int rc;
+    if ((rc = ensure_tmp(ctx, 4, (size_t)nt * sizeof(double) + 4 * sizeof(int)))) return rc;
+    double* d_amax = (double*)ctx->d_tmp[4];
+    int* d_flags = (int*)(d_amax + nt);                               // [has_nan, lower, bw]
+    CK(cudaMemsetAsync(d_flags, 0, 4 * sizeof(int), ctx->stream));
+    weights_absmax_kernel<<<nt, 256, 0, ctx->stream>>>(U_dev, ns, d_amax, d_flags);
+    CKL();
+    weights_structure_kernel<<<nt, 256, 0, ctx->stream>>>(U_dev, ns, d_amax, band_rtol, d_flags + 1, d_flags + 2);
+    CKL();
+    int flags[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flags[0]) return fail(ctx, BEATGPU_E_ARG, "update_weights_dev: NaN in a weight matrix");
+    const bool lower = flags[1] != 0;
+    const int bw = flags[2];
+    int mode;                                                         // same rules as the host path
+    if (lower) mode = MISFIT_DENSE;
+    else if (bw == 0) mode = MISFIT_DIAG;
+    else if (bw <= 32 && bw + 1 < ns / 2) mode = MISFIT_BAND;
+    else mode = MISFIT_DENSE;
+    const size_t n = mode == MISFIT_DIAG ? (size_t)nt * ns : (mode == MISFIT_BAND ? (size_t)nt * (bw + 1) * ns : (size_t)nt * ns * ns);
+    const size_t bytes = n * sizeof(double);
+    if (!w.d_W || w.W_bytes != bytes) {                               // footprint changed: reallocate (stage boundary only)
+        if (w.d_W) { cudaFree(w.d_W); w.d_W = nullptr; w.W_bytes = 0; }
+        CK(cudaMalloc((void**)&w.d_W, bytes));
+        w.W_bytes = bytes;
+    }
+    const int blocks = (int)std::min<size_t>((size_t)ctx->prop.multiProcessorCount * 8, (n + 255) / 256);
+    weights_repack_kernel<<<blocks, 256, 0, ctx->stream>>>(U_dev, w.d_W, nt, ns, mode == MISFIT_DIAG ? 0 : (mode == MISFIT_BAND ? 1 : 2), bw);
+    CKL();
+    if (!w.d_slog_pdet) CK(cudaMalloc((void**)&w.d_slog_pdet, (size_t)nt * sizeof(double)));
+    CK(cudaMemcpyAsync(w.d_slog_pdet, slog_pdet_dev, (size_t)nt * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));                           // the caller may free U_dev right after the call
+    w.misfit_mode = mode; w.bw = bw; w.dense_upper = lower ? 0 : 1;
+    return BEATGPU_OK;
+}
+
 int beatgpu_set_geodetic(beatgpu_ctx* ctx, int nobs, int nds, const int32_t* slo, const int32_t* shi, const double* const* G,
                          const double* data, const double* odw, const double* U_concat, const double* slog_pdet,
                          const int32_t* nsamples, const int32_t* hyper_idx)

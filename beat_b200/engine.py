@@ -97,6 +97,16 @@ class BatchedFFILogLike:
         return self.ctx.alloc_gflib(self.wmap_ids[wmap_index], slipvar_index, self.store_dtype, dims, dur_min, dur_step,
                                     st_min, st_step)
 
+    def update_weights_device(self, wmap_index, U_dev, slog_pdet_dev):
+        """Between SMC stages with the new weights still on the device: contiguous CUDA float64 torch tensors
+        [nt, ns, ns] and [nt] (``covariance.weights_from_residuals_device``); no host round trip."""
+        import torch
+        for x in (U_dev, slog_pdet_dev):
+            if x.dtype != torch.float64 or not x.is_cuda or not x.is_contiguous():
+                raise ValueError("weights must be contiguous CUDA float64 tensors")
+        torch.cuda.current_stream(U_dev.device).synchronize()          # the tensors were produced on torch's stream
+        self.ctx.update_weights_dev(self.wmap_ids[wmap_index], U_dev.data_ptr(), slog_pdet_dev.data_ptr())
+
     def update_weights(self, wmap_index, U, slog_pdet):
         self.ctx.update_weights(self.wmap_ids[wmap_index], U, slog_pdet)
 

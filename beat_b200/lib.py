@@ -87,6 +87,7 @@ _SIGNATURES = {
                                       C.c_double, C.POINTER(_P), C.POINTER(C.c_int64)]),
     "beatgpu_upload_data": (C.c_int, [_P, C.c_int, _P]),
     "beatgpu_update_weights": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
+    "beatgpu_update_weights_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_double]),
     "beatgpu_set_geodetic": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "beatgpu_update_geodetic_weights": (C.c_int, [_P, _P, _P]),
     "beatgpu_set_laplacian": (C.c_int, [_P, _P, C.c_double, C.c_int]),
@@ -249,6 +250,11 @@ class Context:
     def upload_data(self, wmap, data):
         d = _f64(data)
         self._check(self._lib.beatgpu_upload_data(self._h, wmap, _ptr(d)))
+
+    def update_weights_dev(self, wmap, U_dev_ptr, slog_pdet_dev_ptr, band_rtol=-1.0):
+        """Weights already on the device (e.g. torch tensors from covariance.weights_from_residuals_device)."""
+        self._check(self._lib.beatgpu_update_weights_dev(self._h, wmap, C.c_void_p(U_dev_ptr), C.c_void_p(slog_pdet_dev_ptr),
+                                                         band_rtol))
 
     def update_weights(self, wmap, U, slog_pdet, band_rtol=-1.0):
         U, lp = _f64(U), _f64(slog_pdet)

@@ -148,6 +148,13 @@ int beatgpu_upload_data(beatgpu_ctx* ctx, int wmap_id, const double* data /*[nt,
 int beatgpu_update_weights(beatgpu_ctx* ctx, int wmap_id, const double* U /*[nt, ns, ns]*/,
                            const double* slog_pdet /*[nt]*/, double band_rtol);
 
+/* Same for weight matrices that were computed ON the device (the per-stage covariance update from the residuals of
+ * the MAP point, beat/covariance.py:397-427,716-771 -> heart.Covariance.chol_inverse): U_dev [nt, ns, ns] and
+ * slog_pdet_dev [nt] are device pointers; structure detection and repacking run on the device, nothing but three
+ * flags crosses PCIe.  Synchronises before returning (the caller may free its buffers).                    */
+int beatgpu_update_weights_dev(beatgpu_ctx* ctx, int wmap_id, const double* U_dev, const double* slog_pdet_dev,
+                               double band_rtol);
+
 /* Geodetic static composite (beat/models/geodetic.py:1030-1084): one library per slip var,
  * G[var] (npatches, nobs) as GeodeticGFLibrary (beat/ffi/base.py:192-305); data and odw [nobs];
  * n_datasets slices [lo, hi) of the concatenated observation vector (Bij.srmap); U per dataset

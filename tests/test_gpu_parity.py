@@ -412,6 +412,24 @@ def test_get_synthetics_and_stage_weight_update():
     got, _ = ev(Q)
     prob2 = dict(prob, wavemaps=[dict(wm, U=U_host, slog_pdet=lp_host)])
     np.testing.assert_allclose(got, _oracle_logpts(prob2, Q), rtol=1e-7)
+    # the same update without leaving the device (structure detection + repack in kernels): identical results, for
+    # dense, banded and diagonal weights
+    ev.update_weights_device(0, U_dev.contiguous(), lp_dev.contiguous())
+    got_dev, _ = ev(Q)
+    np.testing.assert_array_equal(got_dev, got)
+    for kind in ("band", "diag"):
+        Uk = torch.triu(U_dev) if kind == "band" else torch.diag_embed(torch.diagonal(U_dev, dim1=1, dim2=2))
+        if kind == "band":
+            Uk = Uk - torch.triu(U_dev, diagonal=3)                    # main + two super-diagonals
+        ev.update_weights(0, Uk.cpu().numpy(), lp_dev.cpu().numpy())
+        a, _ = ev(Q)
+        ev.update_weights_device(0, Uk.contiguous(), lp_dev.contiguous())
+        b, _ = ev(Q)
+        np.testing.assert_array_equal(a, b)
+    bad = U_dev.clone()
+    bad[1, 2, 3] = float("nan")
+    with pytest.raises(ValueError, match="NaN"):
+        ev.update_weights_device(0, bad, lp_dev.contiguous())
     ev.close()
 
 
