@@ -725,7 +725,9 @@ int beatgpu_upload_gflib(beatgpu_ctx* ctx, int wmap_id, int var, const void* tra
     // repack kernel (dtype conversion + row padding) of chunk i runs behind it.  A source the caller has already
     // page-locked (beatgpu_host_register) is copied from directly.
     const size_t row_bytes = (size_t)ns * ssz;
-    const size_t chunk_rows = std::max<size_t>(1, ((size_t)64 << 20) / row_bytes);
+    size_t chunk_target = (size_t)64 << 20;
+    if (const char* e = getenv("BEATGPU_UPLOAD_CHUNK_KB")) { long v = atol(e); if (v >= 1) chunk_target = (size_t)v << 10; }   // tests: force many chunks
+    const size_t chunk_rows = std::max<size_t>(1, chunk_target / row_bytes);
     const size_t chunk_bytes = std::min(rows, chunk_rows) * row_bytes;
     if ((rc = ensure_tmp(ctx, 0, chunk_bytes)) || (rc = ensure_tmp(ctx, 1, chunk_bytes))) return rc;
     cudaPointerAttributes attr;
