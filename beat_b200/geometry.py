@@ -18,6 +18,7 @@ from __future__ import annotations
 import numpy as np
 
 from .lib import GEOM_VARS, Context, GeomLayout
+from .ops import HAVE_PYTENSOR, _Apply, _OpBase, _tt
 
 
 class ArrivalTaper(object):
@@ -220,8 +221,9 @@ class BatchedGeometryLogLike:
         self.ctx.close()
 
 
-class SeisSynthesizer(object):
-    """Mirror of the reference Op (beat/pytensorf.py:129-311) for ONE double-couple source: called with a dict of named
+class SeisSynthesizer(_OpBase):
+    """Mirror of the reference Op (beat/pytensorf.py:129-311; a ``pytensor.tensor.Op`` subclass when pytensor is
+    importable, with the reference's dict-taking ``make_node``) for ONE double-couple source: called with a dict of named
     source variables (values scalar / [1] as the reference, or [B] / [B, 1] for a batch of chains) it returns
     ``(synthetics, tmins)`` -- [nt, ns] and [nt] (with a leading chain axis for a batch).  ``tmins`` are the taper's
     lower chop bound per target (beat/heart.py:3729), constant because the arrival times are fixed."""
@@ -265,6 +267,7 @@ class SeisSynthesizer(object):
     def perform(self, node, inputs, output):
         point = {v: np.asarray(i, dtype=np.float64) for v, i in zip(self.varnames, inputs)}
         shifts = point.pop("time_shift", None)
+        point = {v: point[v] for v in GEOM_VARS}                     # input order does not matter (pytensorf.py:133)
         B = max(p.size for p in point.values())
         batched = any(p.ndim >= 1 and p.size > 1 for p in point.values())
         Q = np.zeros((B, self._n_par))
@@ -281,15 +284,27 @@ class SeisSynthesizer(object):
         output[0][0] = synths if batched else synths[0]
         output[1][0] = tmins.copy() if batched else tmins[0].copy()
 
-    def __call__(self, inputs):
-        """``inputs``: dict of named variables, as the reference's ``make_node`` takes (pytensorf.py:215-239)."""
-        missing = [v for v in GEOM_VARS if v not in inputs]
-        if missing:
-            raise KeyError("source variables missing: %s" % ", ".join(missing))
-        self.varnames = list(GEOM_VARS) + (["time_shift"] if self.station_corrections else [])
-        out = [[None], [None]]
-        self.perform(None, [inputs[v] for v in self.varnames], out)
-        return out[0][0], out[1][0]
+    def make_node(self, inputs):  # pragma: no cover - needs pytensor
+        """``inputs``: dict of named tensors, exactly like the reference (pytensorf.py:215-239)."""
+        self.varnames = list(inputs.keys())
+        inlist = [_tt.as_tensor_variable(i) for i in inputs.values()]
+        outm_shape, outv_shape = self.infer_shape()
+        outm = _tt.as_tensor_variable(np.zeros(outm_shape))
+        outv = _tt.as_tensor_variable(np.zeros(outv_shape))
+        return _Apply(self, inlist, [outm.type(), outv.type()])
+
+    if not HAVE_PYTENSOR:
+        def __call__(self, inputs):
+            """Eager call without pytensor: ``inputs`` is the dict of named variables ``make_node`` would take."""
+            missing = [v for v in GEOM_VARS if v not in inputs]
+            if missing:
+                raise KeyError("source variables missing: %s" % ", ".join(missing))
+            if self.station_corrections and "time_shift" not in inputs:
+                raise KeyError("time_shift")
+            self.varnames = list(inputs.keys())
+            out = [[None], [None]]
+            self.perform(None, [inputs[v] for v in self.varnames], out)
+            return out[0][0], out[1][0]
 
     def close(self):
         self._ctx.close()

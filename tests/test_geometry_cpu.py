@@ -225,3 +225,42 @@ def test_oracle_reproduces_reference_driven_golden(name):
         np.testing.assert_allclose(mine, ref[i], rtol=1e-12, atol=1e-18)
         shifts = point["time_shifts"][wm["station_idx"]] if wm.get("station_idx") is not None else 0.0
         np.testing.assert_allclose(g[name + "_tmins"][i], wm["arrival_times"] + shifts + dict(zip("abcd", wm["taper"]))[chop[0]])
+
+
+def test_seis_synthesizer_op_host_logic_without_a_gpu():
+    """The Op mirror's perform(): named inputs in any order, scalar or batched, optional per-target time_shift --
+    checked against a fake context (the CUDA call itself is covered by the GPU tests)."""
+    from beat_b200.geometry import ArrivalTaper, SeisSynthesizer
+    from beat_b200.lib import GEOM_VARS
+
+    class FakeCtx:
+        def geom_synthetics_batch(self, wid, Q, nt, ns):
+            self.Q = Q.copy()
+            return np.broadcast_to(Q[:, :1, None], (Q.shape[0], nt, ns)).copy()
+
+    for sc in (False, True):
+        op = SeisSynthesizer.__new__(SeisSynthesizer)
+        op.nt, op.ns, op.station_corrections = 3, 5, sc
+        op._n_par = len(GEOM_VARS) + (3 if sc else 0)
+        op.arrival_times = np.array([10.0, 20.0, 30.0])
+        op.arrival_taper, op.chop_bounds = ArrivalTaper(-2.0, -1.0, 1.5, 2.5), ("b", "c")
+        op._ctx, op._wid = FakeCtx(), 0
+        vals = {v: float(i + 1) for i, v in enumerate(GEOM_VARS)}
+        inputs = dict(reversed(list(vals.items())))                    # reversed order on purpose
+        if sc:
+            inputs["time_shift"] = np.array([0.5, -0.5, 0.25])
+        synths, tmins = op(inputs)
+        assert synths.shape == (3, 5) and tmins.shape == (3,)
+        np.testing.assert_array_equal(op._ctx.Q[0, :9], np.arange(1.0, 10.0))
+        shift = inputs.get("time_shift", 0.0)
+        np.testing.assert_allclose(tmins, op.arrival_times + shift - 1.0)
+        if sc:
+            np.testing.assert_array_equal(op._ctx.Q[0, 9:], inputs["time_shift"])
+        batch = {v: np.full(4, vals[v]) for v in GEOM_VARS}
+        if sc:
+            batch["time_shift"] = np.tile(inputs["time_shift"], (4, 1))
+        sb, tb = op(batch)
+        assert sb.shape == (4, 3, 5) and tb.shape == (4, 3)
+        with pytest.raises(KeyError):
+            op({k: v for k, v in inputs.items() if k != "depth"})
+    assert op.infer_shape() == [(3, 5), (3,)]
