@@ -19,7 +19,9 @@ PINNED (BEAT side): tests/golden/geometry_golden.npz holds synthetics produced b
 heart.seis_synthetics / get_phase_taperer / update_target_times / post_process_trace / Filter.apply, imported from
 /root/reference (tests/golden/make_geometry_golden.py; pyrocko's Trace and engine replaced by stand-ins): the window the
 reference puts on each target, the order and arguments of highpass / lowpass / extend / taper / chop, the stacking and
-the returned tmins are the reference's, and this module reproduces them bit for bit.
+the returned tmins are the reference's, and this module reproduces them bit for bit.  Two more cases run the
+reference Op itself (pytensorf.SeisSynthesizer.perform: adjust_point_units, split_point, update_source, event-time
+offset, station corrections) with an absolute event time and agree to float32 rounding.
 
 PARITY UNPINNED for the part below the engine.process() call: the arithmetic of the seismogram synthesis, the
 filters and the taper lives in the third-party package **pyrocko** (>= 2023.10.11, reference pyproject.toml:35),

@@ -145,24 +145,74 @@ class GfTarget(_refshim.GutsObject):
 
 # ---------------------------------------------------------------- stand-in engine
 class Engine(object):
-    """process() = the oracle's restated pyrocko synthesis over the window the reference put on each target."""
+    """process() = the oracle's restated pyrocko synthesis over the window the reference put on each target.
+    ``t_event``: absolute origin time of the reference event (a multiple of deltat); the oracle works relative to it."""
 
-    def __init__(self, gprob, wm):
-        self.gprob, self.wm = gprob, wm
+    def __init__(self, gprob, wm, t_event=0.0):
+        self.gprob, self.wm, self.t_event = gprob, wm, t_event
+
+    def get_store(self, store_id):
+        return types.SimpleNamespace(config=types.SimpleNamespace(sample_rate=1.0 / self.gprob["store"]["deltat"]))
+
+    def close_cashed_stores(self):
+        pass
 
     def process(self, sources, targets, nthreads=1):
         gprob, wm, dt = self.gprob, self.wm, self.gprob["store"]["deltat"]
+        i_event = int(round(self.t_event / dt))
         results = []
         for src_obj in sources:
+            params = src_obj.params if hasattr(src_obj, "params") else src_obj.as_oracle_source(self.t_event)
             for t, target in enumerate(targets):
                 # pyrocko seismosizer: itmin = floor(tmin/deltat), nsamples = ceil(tmax/deltat) - itmin + 1
                 itmin = int(math.floor(target.tmin / dt))
                 n = int(math.ceil(target.tmax / dt)) - itmin + 1
-                assert (itmin, n) == O.target_window(wm, t), "reference window != oracle window"
-                raw, it0 = O.seismogram(gprob, wm, t, src_obj.params)
-                assert it0 == itmin and raw.size == n
+                assert (itmin - i_event, n) == O.target_window(wm, t), "reference window != oracle window"
+                raw, it0 = O.seismogram(gprob, wm, t, params)
+                assert it0 == itmin - i_event and raw.size == n
                 results.append((src_obj, target, Trace(itmin * dt, dt, raw)))
         return types.SimpleNamespace(iter_results=lambda: iter(results))
+
+
+class FakeSTF(dict):
+    """pyrocko STF stand-in: utility.update_source writes ``source.stf[k] = v`` for non-source attributes."""
+
+
+class FakeSource(object):
+    """pyrocko gf.DCSource stand-in with the mapping interface utility.update_source uses (keys / __setitem__ / stf)."""
+    _keys = ("east_shift", "north_shift", "depth", "strike", "dip", "rake", "magnitude", "time")
+
+    def __init__(self):
+        self.stf = FakeSTF(duration=0.0)
+        for k in self._keys:
+            setattr(self, k, 0.0)
+
+    def keys(self):
+        return list(self._keys)
+
+    def __setitem__(self, k, v):
+        assert k in self._keys
+        setattr(self, k, v)
+
+    def as_oracle_source(self, t_event):
+        d = {k: getattr(self, k) for k in self._keys}           # already in metres (adjust_point_units ran)
+        d["time"] = self.time - t_event                           # the oracle's times are relative to the event origin
+        d["duration"] = self.stf["duration"]
+        return d
+
+
+class FakeMapping(object):
+    """beat.config.DatatypeParameterMapping stand-in (utility.split_point, beat/utility.py:678-733)."""
+
+    def __init__(self, n_sources):
+        self.n_sources = n_sources
+        self._names = FakeSource._keys + ("duration",)
+
+    def point_to_sources_mapping(self):
+        return {k: list(range(self.n_sources)) for k in self._names}
+
+    def point_variable_names(self):
+        return list(self._names)
 
 
 def main():
@@ -236,6 +286,49 @@ def main():
         n = case["name"]
         out[n + "_Q"], out[n + "_synths"], out[n + "_tmins"] = Q, synths_ref, tmins_ref
         print(n, synths_ref.shape, float(np.abs(synths_ref).max()))
+    # ---- the reference Op itself: pytensorf.SeisSynthesizer.perform (beat/pytensorf.py:241-302) with an absolute event
+    # time, km -> m units (utility.adjust_point_units), split_point / update_source, station corrections
+    from beat import pytensorf
+    t_event = 1.0e6                                              # a multiple of deltat
+    for name, kw in (("op_two_sources", dict(n_stations=2, seed=206, n_sources=2)),
+                     ("op_station_corr", dict(n_stations=3, seed=207, station_corrections=True))):
+        gprob = S.make_geometry_problem(**kw)
+        wm = gprob["wavemaps"][0]
+        a, b, c, d = wm["taper"]
+        n_src = gprob["n_sources"]
+        targets = [heart.DynamicTarget(lat=wm["lats"][t], lon=wm["lons"][t], azimuth=wm["azimuths"][t], dip=wm["dips"][t],
+                                       store_id="synthetic") for t in range(wm["nt"])]
+        f = wm["filterer"][0]
+        Q = S.draw_chains(gprob, 3, seed=400)
+        got = []
+        for q in Q:
+            point = S.split_point(gprob, q)
+            shifts = point["time_shifts"][wm["station_idx"]] if wm.get("station_idx") is not None else None
+            arr_rel = np.array(wm["arrival_times"]) + (shifts if shifts is not None else 0.0)
+            engine = Engine(gprob, dict(wm, arrival_times=arr_rel), t_event=t_event)
+            op = pytensorf.SeisSynthesizer(
+                engine=engine, sources=[FakeSource() for _ in range(n_src)], mapping=FakeMapping(n_src), targets=targets,
+                events=[types.SimpleNamespace(time=t_event)], event_idx=0, arrival_taper=heart.ArrivalTaper(a=a, b=b, c=c, d=d),
+                arrival_times=np.array(wm["arrival_times"]) + t_event, wavename="any_P",
+                filterer=[heart.Filter(lower_corner=f["lower_corner"], upper_corner=f["upper_corner"], order=f["order"])],
+                pre_stack_cut=True, station_corrections=shifts is not None, domain="time")
+            inputs = {k: np.atleast_1d(v) for k, v in point.items() if k not in ("hypers", "time_shifts")}
+            if shifts is not None:
+                inputs["time_shift"] = shifts
+            op.varnames = list(inputs.keys())
+            output = [[None], [None]]
+            op.perform(None, list(inputs.values()), output)
+            synths, tmins = output[0][0], output[1][0]
+            assert op.infer_shape() == [synths.shape, (wm["nt"],)]
+            # not bit-equal: (t_event + t) - t_event differs from t by ~1e-10 s, which moves STF bin weights in the last
+            # float32 digit -- the oracle's relative-time convention against the reference's absolute one
+            mine = O.geometry_synthetics(gprob, point)
+            np.testing.assert_allclose(synths, mine, rtol=2e-6, atol=2e-6 * np.abs(mine).max())
+            np.testing.assert_allclose(np.asarray(tmins) - t_event, arr_rel + b, atol=1e-6)
+            got.append(synths)
+        out[name + "_Q"], out[name + "_synths"] = Q, np.array(got)
+        print(name, np.array(got).shape)
+
     # the sequence of trace operations the reference issued for the default (stepwise) filter, for the record
     tr = Trace(0.0, 0.5, np.random.default_rng(0).standard_normal(200).astype(np.float32))
     heart.post_process_trace(tr, CosTaper(20.0, 25.0, 60.0, 65.0), [heart.Filter(lower_corner=0.01, upper_corner=0.4, order=4)],

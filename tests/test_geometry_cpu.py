@@ -264,3 +264,20 @@ def test_seis_synthesizer_op_host_logic_without_a_gpu():
         with pytest.raises(KeyError):
             op({k: v for k, v in inputs.items() if k != "depth"})
     assert op.infer_shape() == [(3, 5), (3,)]
+
+
+OP_GOLDEN_CASES = {"op_two_sources": dict(n_stations=2, seed=206, n_sources=2),
+                   "op_station_corr": dict(n_stations=3, seed=207, station_corrections=True)}
+
+
+@pytest.mark.parametrize("name", sorted(OP_GOLDEN_CASES))
+def test_oracle_matches_the_reference_op_perform(name):
+    """Golden synthetics produced by the reference's OWN pytensorf.SeisSynthesizer.perform (beat/pytensorf.py:241-302:
+    adjust_point_units, split_point, update_source, event-time offset, station corrections) -> heart.seis_synthetics,
+    run with an absolute event time of 1e6 s (make_geometry_golden.py).  The oracle works relative to the event origin;
+    the two agree to float32 rounding of the STF bin weights."""
+    g = load_geometry_golden()
+    gprob = S.make_geometry_problem(**OP_GOLDEN_CASES[name])
+    for q, ref in zip(g[name + "_Q"], g[name + "_synths"]):
+        mine = O.geometry_synthetics(gprob, S.split_point(gprob, q))
+        np.testing.assert_allclose(mine, ref, rtol=2e-6, atol=2e-6 * np.abs(ref).max())

@@ -427,3 +427,16 @@ def test_two_wavemaps_p_and_s_windows():
         np.testing.assert_allclose(-2.0 * logpts[:, sl] - const, -2.0 * ref[:, sl] - const, rtol=1e-5)
     np.testing.assert_allclose(like, ref.sum(axis=1), rtol=1e-5)
     _assert_synth_close(syn_s, np.array([O.geometry_synthetics(gprob, p, 1) for p in _points(gprob, Q)]))
+
+
+@pytest.mark.parametrize("name", ["op_two_sources", "op_station_corr"])
+def test_cuda_matches_reference_op_perform_golden(name):
+    """CUDA synthetics against golden vectors from the reference's own SeisSynthesizer.perform (absolute event time,
+    unit conversion, source update, station corrections; tests/golden/make_geometry_golden.py)."""
+    from test_geometry_cpu import OP_GOLDEN_CASES, load_geometry_golden
+    g = load_geometry_golden()
+    gprob = S.make_geometry_problem(**OP_GOLDEN_CASES[name])
+    ev = _engine(gprob)
+    got = ev.get_synthetics(g[name + "_Q"])
+    ev.close()
+    _assert_synth_close(got, g[name + "_synths"])
