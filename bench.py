@@ -269,7 +269,19 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.nvml = pynvml
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.handle = None
+            try:        # CUDA_VISIBLE_DEVICES may renumber devices: resolve the NVML handle through the device's UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                try:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+                except TypeError:
+                    self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                self.handle = None
+            if self.handle is None:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
             self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
             try:
                 self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.handle) / 1000.0
