@@ -67,3 +67,11 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "libfsport" not in text, f
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md is the reference-side binding guide: every exported entry must appear there (host/_dev pairs may
+    share a row)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared_symbols() if n not in doc and n.replace("_dev", "") not in doc]
+    assert not missing, missing
