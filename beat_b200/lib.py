@@ -153,6 +153,13 @@ def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def _check_q(q, n_params, what):
+    """The C entries trust [B, n_params]: a parameter matrix of another width must never reach them."""
+    if q.ndim != 2 or (n_params is not None and q.shape[1] != n_params):
+        raise ValueError("%s: q must be [B, %s], got %s" % (what, n_params, q.shape))
+    return q
+
+
 class Context:
     """One libbeatgpu context = one (process, GPU).  Thin, typed wrappers over the C entry points."""
 
@@ -217,6 +224,7 @@ class Context:
     def set_layout(self, layout: Layout, fixed=None):
         fx = None if fixed is None else _f64(fixed)
         self._check(self._lib.beatgpu_set_layout(self._h, C.byref(layout), _ptr(fx)))
+        self._n_params = layout.n_params
 
     def add_wavemap(self, n_targets, n_samples, interpolation, station_idx, hyper_idx, nsamples):
         st = None if station_idx is None else _i32(station_idx)
@@ -325,7 +333,7 @@ class Context:
 
     def ffi_loglike_batch(self, q, logpts=None, like=None):
         """Host-pointer entry (copies in and out, synchronises).  q [B, n_params] float64 C-contiguous."""
-        q = _f64(q)
+        q = _check_q(_f64(q), getattr(self, "_n_params", None), "ffi_loglike_batch")
         B = q.shape[0]
         n_out = self.n_outputs()
         if logpts is None:
@@ -346,7 +354,7 @@ class Context:
                                                             C.c_void_p(like_dev_ptr or 0)))
 
     def ffi_synthetics_batch(self, wmap, q, nt, ns):
-        q = _f64(q)
+        q = _check_q(_f64(q), getattr(self, "_n_params", None), "ffi_synthetics_batch")
         out = np.empty((q.shape[0], nt, ns))
         self._check(self._lib.beatgpu_ffi_synthetics_batch(self._h, wmap, q.shape[0], _ptr(q), _ptr(out)))
         return out
@@ -430,7 +438,7 @@ class Context:
         return wid.value
 
     def geom_loglike_batch(self, Q):
-        Q = _f64(Q)
+        Q = _check_q(_f64(Q), getattr(self, "_geom_n_params", None), "geom_loglike_batch")
         B = Q.shape[0]
         n_out = self.n_outputs()
         logpts, like = np.empty((B, n_out)), np.empty(B)
@@ -446,7 +454,7 @@ class Context:
                                                              C.c_void_p(like_ptr or 0)))
 
     def geom_synthetics_batch(self, wmap, Q, nt, ns):
-        Q = _f64(Q)
+        Q = _check_q(_f64(Q), getattr(self, "_geom_n_params", None), "geom_synthetics_batch")
         out = np.empty((Q.shape[0], nt, ns))
         self._check(self._lib.beatgpu_geom_synthetics_batch(self._h, wmap, Q.shape[0], _ptr(Q), _ptr(out)))
         return out

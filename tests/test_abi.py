@@ -75,3 +75,16 @@ def test_integration_doc_lists_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [n for n in _declared_symbols() if n not in doc and n.replace("_dev", "") not in doc]
     assert not missing, missing
+
+
+def test_parameter_matrix_width_is_checked_before_the_c_call():
+    """The C entries trust [B, n_params]; the binding refuses any other width (no device needed to check that)."""
+    from beat_b200.lib import Context
+    c = Context.__new__(Context)
+    c._n_params, c._geom_n_params = 7, 10
+    c.n_outputs = lambda: 3
+    import numpy as np
+    for fn, args in ((c.ffi_loglike_batch, (np.zeros((4, 6)),)), (c.ffi_synthetics_batch, (0, np.zeros((4, 8)), 2, 5)),
+                     (c.geom_loglike_batch, (np.zeros((4, 9)),)), (c.geom_synthetics_batch, (0, np.zeros(10), 2, 5))):
+        with pytest.raises(ValueError, match="q must be"):
+            fn(*args)
