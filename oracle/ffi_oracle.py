@@ -19,6 +19,9 @@ Pinning status
   (``tests/golden/make_golden.py``; pytensor/pyrocko are absent there, so the script installs
   numpy-backed stand-ins for the handful of symbols those modules touch at import/call time --
   the arithmetic that runs is the reference's own source).
+* composite level: ``ffi_seismic_eval(return_synth=True)`` reproduces, to 1e-9, synthetics of the reference's own
+  ``SeismicDistributerComposite.get_synthetics`` + ``FaultGeometry.point2starttimes`` (numpy fast sweep)
+  for one / two subfaults with station corrections (``tests/golden/make_ffi_composite_golden.py``).
 """
 from __future__ import annotations
 

@@ -579,3 +579,19 @@ def test_misfit_batch_dev_long_traces():
     ctx.misfit_batch_dev(wid, B, r_d.data_ptr(), h_d.data_ptr(), nt, out.data_ptr())
     assert np.array_equal(out.cpu().numpy(), host)
     ctx.close()
+
+
+@pytest.mark.parametrize("name", ["one_fault_ml", "one_fault_nn_corr", "two_faults_ml_corr"])
+def test_cuda_synthetics_match_reference_composite_golden(name):
+    """CUDA forward model (sweep + stacking, f64 library) against synthetics produced by the reference's own
+    SeismicDistributerComposite.get_synthetics / FaultGeometry.point2starttimes (committed fixture
+    tests/golden/ffi_composite_golden.npz, generated by tests/golden/make_ffi_composite_golden.py); no oracle in the loop."""
+    from test_oracle_golden import FFI_COMPOSITE_CASES, load_ffi_composite_golden
+    from beat_b200.engine import BatchedFFILogLike
+    g = load_ffi_composite_golden()
+    prob = synthetic.make_problem(**FFI_COMPOSITE_CASES[name])
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    got = ev.get_synthetics(g[name + "_Q"])
+    ev.close()
+    ref = g[name + "_synths"]
+    np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-8 * np.abs(ref).max())

@@ -174,3 +174,31 @@ def test_weights_from_residuals_torch_cpu(golden):
     for i in range(3):
         # U is unique up to nothing (Cholesky with positive diagonal): compare directly and through U^T U = C^-1
         np.testing.assert_allclose(U[i].numpy(), Uh[i], rtol=1e-6, atol=1e-7 * np.abs(Uh[i]).max())
+
+
+FFI_COMPOSITE_CASES = {
+    "one_fault_ml": dict(nt=4, subfaults=((4, 6, 2.0),), ns=24, ndur=4, seed=301, interpolation="multilinear"),
+    "one_fault_nn_corr": dict(nt=5, subfaults=((3, 5, 2.5),), ns=20, ndur=3, seed=302, interpolation="nearest_neighbor",
+                              station_corrections=True),
+    "two_faults_ml_corr": dict(nt=3, subfaults=((3, 4, 2.0), (2, 5, 2.0)), ns=16, ndur=4, seed=303, interpolation="multilinear",
+                               station_corrections=True),
+}
+
+
+def load_ffi_composite_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ffi_composite_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(FFI_COMPOSITE_CASES))
+def test_oracle_matches_reference_composite_synthetics(name):
+    """tests/golden/ffi_composite_golden.npz: synthetics from the reference's OWN
+    SeismicDistributerComposite.get_synthetics (beat/models/seismic.py:1351-1507) with FaultGeometry.point2starttimes
+    (numpy fast sweep), station corrections and SeismicGFLibrary.stack_all per slip component
+    (tests/golden/make_ffi_composite_golden.py).  The oracle's composite evaluation must reproduce them."""
+    from beat_b200 import synthetic
+    g = load_ffi_composite_golden()
+    prob = synthetic.make_problem(**FFI_COMPOSITE_CASES[name])
+    for q, ref in zip(g[name + "_Q"], g[name + "_synths"]):
+        _, mine, _ = O.ffi_seismic_eval(prob, synthetic.split_point(prob, q), impl="auto", return_synth=True)
+        np.testing.assert_allclose(mine[0], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
