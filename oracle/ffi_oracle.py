@@ -21,7 +21,9 @@ Pinning status
   the arithmetic that runs is the reference's own source).
 * composite level: ``ffi_seismic_eval(return_synth=True)`` reproduces, to 1e-9, synthetics of the reference's own
   ``SeismicDistributerComposite.get_synthetics`` + ``FaultGeometry.point2starttimes`` (numpy fast sweep)
-  for one / two subfaults with station corrections (``tests/golden/make_ffi_composite_golden.py``).
+  for one / two subfaults with station corrections (``tests/golden/make_ffi_composite_golden.py``), and, to 1e-10,
+  the per-dataset logpts of the reference's own production graph ``SeismicDistributerComposite.get_formula`` run eagerly
+  (Sweeper Op -> compiled fast_sweep_ext, pytensor-mode stack_all, multivariate_normal_chol; same script).
 """
 from __future__ import annotations
 

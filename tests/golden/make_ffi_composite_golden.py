@@ -113,6 +113,74 @@ def main():
             np.testing.assert_allclose(mine[0], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
         out[name + "_Q"], out[name + "_synths"] = Q, synths
         print(name, synths.shape, float(np.abs(synths).max()))
+    # ------------------------------------------------------------------------------------------------------------
+    # The production graph itself: SeismicDistributerComposite.get_formula (beat/models/seismic.py:1210-1349), executed
+    # eagerly through the numpy-backed pytensor shim: the reference's Sweeper Op -> compiled fast_sweep_ext, station
+    # corrections with tt.tile / tt.repeat, stack_all in PYTENSOR mode (tt.batched_dot), residuals, and
+    # multivariate_normal_chol -> per-dataset logpts ("seis_like") and their sum.
+    from beat import pytensorf
+    captured = {}
+
+    def deterministic(name, var):
+        captured[name] = np.asarray(var)
+        return var
+    rseismic.Deterministic = deterministic
+    for name, kw in CASES.items():
+        for hp_specific in (False, True):
+            prob = S.make_problem(hp_specific=hp_specific, **kw)
+            wm = prob["wavemaps"][0]
+            libs = {}
+            for v in prob["slip_vars"]:
+                cfg = SeismicGFLibraryConfig(dimensions=wm["G"][v].shape, starttime_min=wm["st_min"], starttime_sampling=wm["st_step"],
+                                             duration_min=wm["dur_min"], duration_sampling=wm["dur_step"])
+                lib = ffibase.SeismicGFLibrary(config=cfg)
+                lib._gfmatrix = wm["G"][v]
+                lib._tmins = np.zeros(wm["nt"])
+                lib._sgfmatrix = wm["G"][v].view(_refshim._ND)            # what init_optimization would share (ffi/base.py:387-404)
+                lib.spatchidxs = lib.patchidxs
+                lib._stack_switch = {"numpy": wm["G"][v], "pytensor": lib._sgfmatrix}
+                lib.set_stack_mode("pytensor")
+                lib.init_optimization = lambda: None
+                libs[v] = lib
+            corr = bool(prob.get("n_time_shifts"))
+            fault = object.__new__(Fault)
+            Fault.__init__(fault, prob["subfaults"])
+            # datasets carry the log-determinant the way heart.Covariance does (shared scalar ``slog_pdet``, heart.py:130,247-253)
+            datasets = [types.SimpleNamespace(samples=int(wm["nsamples"][t]), typ="any_P_0_Z",
+                                              covariance=types.SimpleNamespace(slog_pdet=np.float64(wm["slog_pdet"][t])))
+                        for t in range(wm["nt"])]
+            Q = S.draw_chains(prob, 5, seed=600)
+            logpts_ref, like_ref = [], []
+            for q in Q:
+                p = S.split_point(prob, q)
+                wmap = types.SimpleNamespace(
+                    n_t=wm["nt"], _mapid="any_P_0", time_shifts_id="time_shifts_any_P_0", station_correction_idxs=wm["station_idx"],
+                    prepare_data=lambda **k: None, shared_data_array=wm["data"], datasets=datasets, weights=list(wm["U"]),
+                    config=types.SimpleNamespace(interpolation=wm["interpolation"], event_idx=0, domain="time", name="any_P",
+                                                 arrival_taper=types.SimpleNamespace(nsamples=lambda sample_rate, ns=wm["ns"]: ns)))
+                comp = types.SimpleNamespace(
+                    name="seismic", _like_name="seis_like", fault=fault, wavemaps=[wmap], gfs=libs, slip_varnames=list(prob["slip_vars"]),
+                    sweepers=[pytensorf.Sweeper(h, nd, nstr, "c") for nd, nstr, h in prob["subfaults"]],
+                    hierarchicals={"time_shifts_any_P_0": np.array(p["time_shifts"])} if corr else {},
+                    events=[None], engine=None, load_gfs=lambda **k: None, analyse_noise=lambda *a, **k: None,
+                    init_weights=lambda: None, get_all_station_names=lambda: [None] * wm["nt"],
+                    get_gflibrary_key=lambda crust_ind, wavename, component: component,
+                    config=types.SimpleNamespace(station_corrections=corr, dataset_specific_residual_noise_estimation=hp_specific,
+                                                 gf_config=types.SimpleNamespace(reference_model_idx=0, sample_rate=1.0 / prob["dt"])))
+                input_rvs = {k: np.array(v, dtype=np.float64) for k, v in p.items() if k not in ("hypers", "time_shifts")}
+                hyper = {"h_any_P_0_Z": np.array(p["hypers"][wm["hyper_idx"]]) if hp_specific else np.float64(p["hypers"][wm["hyper_idx"][0]])}
+                total = rseismic.SeismicDistributerComposite.get_formula(
+                    comp, input_rvs, {}, hyper, types.SimpleNamespace(get_test_point=lambda: {}))
+                logpts_ref.append(captured["seis_like"].copy())
+                like_ref.append(float(total))
+            logpts_ref = np.array(logpts_ref)
+            for q, ref in zip(Q, logpts_ref):
+                mine = O.ffi_seismic_eval(prob, S.split_point(prob, q), impl="ref")
+                np.testing.assert_allclose(mine, ref, rtol=1e-10)
+            np.testing.assert_allclose(like_ref, logpts_ref.sum(axis=1), rtol=1e-12)
+            tag = name + ("_hps" if hp_specific else "")
+            out["formula_" + tag + "_Q"], out["formula_" + tag + "_logpts"] = Q, logpts_ref
+            print("formula", tag, logpts_ref.shape, float(logpts_ref.min()), float(logpts_ref.max()))
     np.savez_compressed(os.path.join(HERE, "ffi_composite_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "ffi_composite_golden.npz"))
 

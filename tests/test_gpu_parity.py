@@ -595,3 +595,20 @@ def test_cuda_synthetics_match_reference_composite_golden(name):
     ev.close()
     ref = g[name + "_synths"]
     np.testing.assert_allclose(got, ref, rtol=1e-8, atol=1e-8 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name,hp_specific", [(n, h) for n in ("one_fault_ml", "one_fault_nn_corr", "two_faults_ml_corr") for h in (False, True)])
+def test_cuda_loglike_matches_reference_get_formula_golden(name, hp_specific):
+    """The fused CUDA evaluation (f64 library) against per-dataset logpts produced by the reference's own production
+    graph SeismicDistributerComposite.get_formula, run eagerly (committed fixture tests/golden/ffi_composite_golden.npz,
+    tests/golden/make_ffi_composite_golden.py); no oracle in the loop."""
+    from test_oracle_golden import FFI_COMPOSITE_CASES, load_ffi_composite_golden
+    from beat_b200.engine import BatchedFFILogLike
+    g = load_ffi_composite_golden()
+    tag = "formula_" + name + ("_hps" if hp_specific else "")
+    prob = synthetic.make_problem(hp_specific=hp_specific, **FFI_COMPOSITE_CASES[name])
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    logpts, like = ev(g[tag + "_Q"])
+    ev.close()
+    np.testing.assert_allclose(logpts, g[tag + "_logpts"], rtol=1e-8)
+    np.testing.assert_allclose(like, g[tag + "_logpts"].sum(axis=1), rtol=1e-8)

@@ -202,3 +202,21 @@ def test_oracle_matches_reference_composite_synthetics(name):
     for q, ref in zip(g[name + "_Q"], g[name + "_synths"]):
         _, mine, _ = O.ffi_seismic_eval(prob, synthetic.split_point(prob, q), impl="auto", return_synth=True)
         np.testing.assert_allclose(mine[0], ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+FORMULA_CASES = [(n, hps) for n in sorted(FFI_COMPOSITE_CASES) for hps in (False, True)]
+
+
+@pytest.mark.parametrize("name,hp_specific", FORMULA_CASES)
+def test_oracle_matches_reference_get_formula(name, hp_specific):
+    """Golden per-dataset logpts from the reference's OWN production graph, SeismicDistributerComposite.get_formula
+    (beat/models/seismic.py:1210-1349), executed eagerly through the numpy-backed pytensor shim: Sweeper Op -> compiled
+    fast_sweep_ext, station corrections, stack_all in pytensor mode (batched_dot), residuals,
+    multivariate_normal_chol with scalar and dataset-specific hyperparameters (make_ffi_composite_golden.py)."""
+    from beat_b200 import synthetic
+    g = load_ffi_composite_golden()
+    tag = "formula_" + name + ("_hps" if hp_specific else "")
+    prob = synthetic.make_problem(hp_specific=hp_specific, **FFI_COMPOSITE_CASES[name])
+    for q, ref in zip(g[tag + "_Q"], g[tag + "_logpts"]):
+        mine = O.ffi_seismic_eval(prob, synthetic.split_point(prob, q), impl="auto")
+        np.testing.assert_allclose(mine, ref, rtol=1e-10)
