@@ -28,10 +28,22 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
+def source_hash():
+    """sha256 over the sources libbeatgpu.so is built from (first 16 hex digits): compiled into the library
+    (beatgpu_source_hash) so that a committed ncu traffic record can be matched against the running build."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in sorted(DEPS):
+        h.update(os.path.basename(d).encode())
+        h.update(open(d, "rb").read())
+    return h.hexdigest()[:16]
+
+
 def build(force=False, verbose=False, extra_flags=()):
     if not force and up_to_date():
         return OUT
-    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-I", os.path.join(ROOT, "include"), "-o", OUT, SRC]
+    cmd = [find_nvcc()] + NVCC_FLAGS + list(extra_flags) + ["-DBEATGPU_SRC_HASH=\"%s\"" % source_hash(),
+                                                            "-I", os.path.join(ROOT, "include"), "-o", OUT, SRC]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

@@ -142,8 +142,17 @@ struct beatgpu_ctx {
     int geo_mode = 1;               // 1 = FP64 tensor-core GEMM tiles (BEATGPU_GEO_MODE=mma), 0 = one CTA per (chain, dataset)
     double* d_partial = nullptr;    // [B, nt, nchunk, ns] scratch of the chunked path
     size_t partial_bytes = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // event pair of the LAST evaluation (aliases into the ring below)
     bool ev_valid = false;
+    // ring of event pairs: one per fused evaluation, so the kernels' share of a timed loop can be summed afterwards
+    std::vector<cudaEvent_t> tev;                  // 2 * kTimingRing events, created on first use
+    int tev_next = 0, tev_pending = 0;             // next slot; evaluations recorded since the last reset (<= kTimingRing)
+    double l2_frac = 0.4;                          // BEATGPU_L2_FRAC: share of L2 one patch chunk of the library may span
+    bool chunk_forced = false;                     // BEATGPU_CHUNK given: no L2-derived chunk
+    cudaStream_t copy_stream = nullptr;            // second stream of the host-pointer entry (q columns behind the sweep)
+    cudaEvent_t copy_done = nullptr, copy_go = nullptr;
+    int split_h2d = 1;                             // BEATGPU_SPLIT_H2D=0: one plain copy of q
+    cudaEvent_t wait_before_stack = nullptr;       // set by the host-pointer entry: the columns of q the stacking needs arrive on copy_stream
     // geometry mode
     std::vector<GeomStore> gstores;
     std::vector<GeomWaveMap> gwmaps;
@@ -334,14 +343,66 @@ int launch_chunk_nvar(beatgpu_ctx* ctx, const ChunkArgs& ca)
     return BEATGPU_OK;
 }
 
+constexpr int kTimingRing = 1024;
+
+bool stream_capturing(beatgpu_ctx* ctx)
+{
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &st) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return st != cudaStreamCaptureStatusNone;
+}
+
+// event pair around the dominant kernels of one evaluation (skipped while the stream is being captured into a graph)
+int timing_begin(beatgpu_ctx* ctx)
+{
+    if (stream_capturing(ctx)) { ctx->ev0 = ctx->ev1 = nullptr; return BEATGPU_OK; }
+    if (ctx->tev.empty()) {
+        ctx->tev.assign(2 * kTimingRing, nullptr);
+        for (auto& e : ctx->tev) CK(cudaEventCreate(&e));
+    }
+    ctx->ev0 = ctx->tev[2 * ctx->tev_next];
+    ctx->ev1 = ctx->tev[2 * ctx->tev_next + 1];
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return BEATGPU_OK;
+}
+
+int timing_end(beatgpu_ctx* ctx)
+{
+    if (!ctx->ev1) return BEATGPU_OK;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->tev_next = (ctx->tev_next + 1) % kTimingRing;
+    ctx->tev_pending = std::min(ctx->tev_pending + 1, kTimingRing);
+    ctx->ev_valid = true;
+    return BEATGPU_OK;
+}
+
+// Patches per chunk of the chunked stacking pass.  All chains stream through one (target, chunk) slice of the library
+// while it is L2 resident, so the slice -- chunk * nvar * ndur * nst * ld * sizeof(T) bytes -- must stay well below the
+// L2 size: 40 % of cudaDeviceProp.l2CacheSize (the partial-synthetic stores and the other operands share the cache),
+// at most kChunkMax (one lane plans one patch), and not so small that the partials scratch explodes (<= 24 chunks).
+void derive_chunk(const beatgpu_ctx* ctx, const WaveMap& w, int nvar, int np, int* chunk, int* nchunk, int64_t* chunk_bytes)
+{
+    const int64_t esz = (w.store_dtype == BEATGPU_F32) ? 4 : 8;
+    const int64_t per_patch = (int64_t)nvar * w.dims[2] * w.dims[3] * w.ld * esz;
+    int target = ctx->chunk_patches;
+    if (!ctx->chunk_forced) {
+        const double budget = ctx->l2_frac * (double)ctx->prop.l2CacheSize;
+        target = (int)std::max<int64_t>(1, std::min<int64_t>(kChunkMax, (int64_t)(budget / (double)std::max<int64_t>(1, per_patch))));
+        const int min_chunk = (np + 23) / 24;                   // keep the [B, nt, nchunk, ns] scratch bounded
+        target = std::max(target, std::min(kChunkMax, min_chunk));
+    }
+    const int nch0 = (np + target - 1) / target;
+    *chunk = (np + nch0 - 1) / nch0;                            // balanced chunks
+    *nchunk = (np + *chunk - 1) / *chunk;
+    if (chunk_bytes) *chunk_bytes = (int64_t)(*chunk) * per_patch;
+}
+
 // chunked path: partial synthetics per (chain, target, patch chunk), then residual + misfit
 int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
 {
     ChunkArgs ca;
     ca.s = a;
-    const int nch0 = (a.np + ctx->chunk_patches - 1) / ctx->chunk_patches;
-    ca.chunk = (a.np + nch0 - 1) / nch0;                 // balanced chunks
-    ca.nchunk = (a.np + ca.chunk - 1) / ca.chunk;
+    derive_chunk(ctx, w, a.nvar, a.np, &ca.chunk, &ca.nchunk, nullptr);
     const size_t need = (size_t)a.B * a.nt * ca.nchunk * a.ns * sizeof(double);
     if (ctx->partial_bytes < need) {
         if (ctx->d_partial) cudaFree(ctx->d_partial);
@@ -486,8 +547,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMalloc((void**)&c->d_viol, sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaMemset(c->d_viol, 0, sizeof(unsigned long long))) != cudaSuccess ||
-        (e = cudaEventCreate(&c->ev0)) != cudaSuccess || (e = cudaEventCreate(&c->ev1)) != cudaSuccess) {
+        (e = cudaMemset(c->d_viol, 0, sizeof(unsigned long long))) != cudaSuccess) {
         int rc = fail(nullptr, BEATGPU_E_CUDA, "context setup failed: %s", cudaGetErrorString(e));
         delete c;
         return rc;
@@ -501,7 +561,9 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_GEO_MODE")) c->geo_mode = (strcmp(e, "simple") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     if (const char* e = getenv("BEATGPU_FILTER_CAP")) { int v = atoi(e); if (v == 80 || v == 0) c->filter_cap = v; }
     if (const char* e = getenv("BEATGPU_GEOM_HALF")) { int v = atoi(e); if (v >= 2 && v <= 4) c->geom_half = v; }
-    if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) c->chunk_patches = v; }
+    if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) { c->chunk_patches = v; c->chunk_forced = true; } }
+    if (const char* e = getenv("BEATGPU_L2_FRAC")) { double v = atof(e); if (v > 0.0 && v <= 4.0) c->l2_frac = v; }
+    if (const char* e = getenv("BEATGPU_SPLIT_H2D")) c->split_h2d = atoi(e) != 0;
     *out = c;
     return BEATGPU_OK;
 }
@@ -534,8 +596,10 @@ void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
     }
     cudaFree(ctx->d_gfixed); cudaFree(ctx->d_rplan); cudaFree(ctx->d_cplan); cudaFree(ctx->d_rawT); cudaFree(ctx->d_gmean);
     cudaFree(ctx->d_gerr);
-    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (auto e : ctx->tev) if (e) cudaEventDestroy(e);
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->copy_go) cudaEventDestroy(ctx->copy_go);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1054,6 +1118,7 @@ int beatgpu_stack_batch(beatgpu_ctx* ctx, int wmap_id, int B, int nvar, const do
     if ((rc = ensure_tmp(ctx, 0, b_dur)) || (rc = ensure_tmp(ctx, 1, b_st)) || (rc = ensure_tmp(ctx, 2, b_sl)) ||
         (rc = ensure_tmp(ctx, 3, b_out)))
         return rc;
+    CK(cudaMemsetAsync(ctx->d_viol, 0, sizeof(unsigned long long), ctx->stream));      // violations are reported per call
     CK(cudaMemcpyAsync(ctx->d_tmp[0], durations, b_dur, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tmp[1], starttimes, b_st, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tmp[2], slips, b_sl, cudaMemcpyHostToDevice, ctx->stream));
@@ -1185,6 +1250,43 @@ static void wire_chain_inputs(beatgpu_ctx* ctx, const WaveMap& w, const double* 
     }
 }
 
+// Host-pointer entry: q [B, n_params] -> ctx->d_q in two phases.  The rupture sweep reads only velocities, nucleation
+// point and time (a quarter of a chain's row at C3), so those columns go first on the ctx stream (strided 2-D copy) and
+// the sweep starts behind them while the slips / durations / hypers columns are still crossing PCIe on a second stream;
+// the stacking pass waits for them through an event.
+static int upload_q_split(beatgpu_ctx* ctx, int B, const double* q)
+{
+    const beatgpu_layout& L = ctx->layout;
+    const int np = ctx->np_total, nsf = ctx->nsf, n = L.n_params;
+    const size_t pitch = (size_t)n * sizeof(double);
+    int lo = n, hi = 0;
+    const int offs[4] = {L.off_velocities, L.off_nucleation_strike, L.off_nucleation_dip, L.off_time};
+    const int lens[4] = {np, nsf, nsf, nsf};
+    for (int i = 0; i < 4; ++i) if (offs[i] >= 0) { lo = std::min(lo, offs[i]); hi = std::max(hi, offs[i] + lens[i]); }
+    const bool split = ctx->split_h2d && !ctx->wmaps.empty() && hi > lo && (hi - lo) * 2 <= n && B >= 64;
+    if (!split) {
+        CK(cudaMemcpyAsync(ctx->d_q, q, (size_t)B * pitch, cudaMemcpyHostToDevice, ctx->stream));
+        return BEATGPU_OK;
+    }
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->copy_go, cudaEventDisableTiming));
+    }
+    CK(cudaEventRecord(ctx->copy_go, ctx->stream));                      // d_q is free once earlier work on the ctx stream is done
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_go, 0));
+    CK(cudaMemcpy2DAsync(ctx->d_q + lo, pitch, q + lo, pitch, (size_t)(hi - lo) * sizeof(double), (size_t)B,
+                         cudaMemcpyHostToDevice, ctx->stream));
+    if (lo > 0)
+        CK(cudaMemcpy2DAsync(ctx->d_q, pitch, q, pitch, (size_t)lo * sizeof(double), (size_t)B, cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (hi < n)
+        CK(cudaMemcpy2DAsync(ctx->d_q + hi, pitch, q + hi, pitch, (size_t)(n - hi) * sizeof(double), (size_t)B, cudaMemcpyHostToDevice,
+                             ctx->copy_stream));
+    CK(cudaEventRecord(ctx->copy_done, ctx->copy_stream));
+    ctx->wait_before_stack = ctx->copy_done;
+    return BEATGPU_OK;
+}
+
 // the fused path, everything on the device
 int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, double* logpts, double* like)
 {
@@ -1208,9 +1310,15 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
 
     if (!ctx->wmaps.empty()) {
         if ((rc = run_sweep(ctx, B, q))) return rc;
-
+    }
+    if (ctx->wait_before_stack) {                    // host-pointer entry: the remaining columns of q arrive on the copy stream
+        cudaEvent_t ev = ctx->wait_before_stack;
+        ctx->wait_before_stack = nullptr;
+        CK(cudaStreamWaitEvent(ctx->stream, ev, 0));
+    }
+    if (!ctx->wmaps.empty()) {
         // ---- per wavemap: gather + stack + residual + misfit (seismic.py:1275-1343)
-        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        if ((rc = timing_begin(ctx))) return rc;
         for (auto& w : ctx->wmaps) {
             StackArgs a;
             memset(&a, 0, sizeof(a));
@@ -1221,13 +1329,13 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
             a.logpts = logpts; a.logpts_sc = n_out; a.out_ofs = w.out_ofs;
             a.synth = nullptr; a.chain_bad = ctx->d_bad; a.violations = ctx->d_viol;
             // the chunked path needs a scratch of B*nt*nchunk*ns doubles; fall back to the fused kernel beyond 8 GiB
-            const size_t nchunk_est = (size_t)(ctx->np_total + ctx->chunk_patches - 1) / ctx->chunk_patches + 1;
-            const bool chunked = ctx->stack_mode == 1 && ctx->np_total > ctx->chunk_patches &&
-                                 (size_t)B * w.nt * nchunk_est * w.ns * sizeof(double) <= ((size_t)8 << 30);
+            int chunk_p = 0, nchunk_p = 0;
+            derive_chunk(ctx, w, L.n_slipvars, ctx->np_total, &chunk_p, &nchunk_p, nullptr);
+            const bool chunked = ctx->stack_mode == 1 && nchunk_p > 1 &&
+                                 (size_t)B * w.nt * nchunk_p * w.ns * sizeof(double) <= ((size_t)8 << 30);
             if ((rc = chunked ? launch_stack_chunked(ctx, w, a) : launch_stack<false>(ctx, w, a))) return rc;
         }
-        CK(cudaEventRecord(ctx->ev1, ctx->stream));
-        ctx->ev_valid = true;
+        if ((rc = timing_end(ctx))) return rc;
     }
 
     if (ctx->geo.set && ctx->geo_mode == 1) {
@@ -1323,7 +1431,10 @@ int beatgpu_ffi_loglike_batch(beatgpu_ctx* ctx, int B, const double* q, double* 
     int rc;
     if ((rc = ensure_scratch(ctx, B))) return rc;
     const int n_out = n_outputs(ctx);
-    CK(cudaMemcpyAsync(ctx->d_q, q, (size_t)B * ctx->layout.n_params * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // violations are reported per call: what earlier device-pointer evaluations (a sampler's rejected proposals) counted
+    // is not this call's business
+    CK(cudaMemsetAsync(ctx->d_viol, 0, sizeof(unsigned long long), ctx->stream));
+    if ((rc = upload_q_split(ctx, B, q))) return rc;
     if ((rc = beatgpu_ffi_loglike_batch_dev(ctx, B, ctx->d_q, ctx->d_logpts, ctx->d_like))) return rc;
     CK(cudaMemcpyAsync(logpts, ctx->d_logpts, (size_t)B * n_out * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (like) CK(cudaMemcpyAsync(like, ctx->d_like, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1341,6 +1452,7 @@ int beatgpu_ffi_synthetics_batch(beatgpu_ctx* ctx, int wmap_id, int B, const dou
     if ((rc = ensure_scratch(ctx, B))) return rc;
     const size_t b_out = (size_t)B * w.nt * w.ns * sizeof(double);
     if ((rc = ensure_tmp(ctx, 3, b_out))) return rc;
+    CK(cudaMemsetAsync(ctx->d_viol, 0, sizeof(unsigned long long), ctx->stream));      // violations are reported per call
     CK(cudaMemcpyAsync(ctx->d_q, q, (size_t)B * ctx->layout.n_params * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = run_sweep(ctx, B, ctx->d_q))) return rc;
     StackArgs a;
@@ -1386,11 +1498,54 @@ int beatgpu_launch_count(beatgpu_ctx* ctx, int64_t* n)
 int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms)
 {
     if (!ctx || !ms) return BEATGPU_E_ARG;
-    if (!ctx->ev_valid) return fail(ctx, BEATGPU_E_NOTREADY, "last_stack_ms: no fused evaluation yet");
+    if (!ctx->ev_valid || !ctx->ev1) return fail(ctx, BEATGPU_E_NOTREADY, "last_stack_ms: no (uncaptured) fused evaluation yet");
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
     return BEATGPU_OK;
 }
+
+int beatgpu_stack_ms_accum(beatgpu_ctx* ctx, int reset, double* sum_ms, int64_t* n_evals)
+{
+    if (!ctx || !sum_ms || !n_evals) return BEATGPU_E_ARG;
+    *sum_ms = 0.0;
+    *n_evals = 0;
+    const int n = ctx->tev_pending;
+    if (n > 0) {
+        CK(cudaSetDevice(ctx->device));
+        const int last = (ctx->tev_next + kTimingRing - 1) % kTimingRing;
+        CK(cudaEventSynchronize(ctx->tev[2 * last + 1]));
+        for (int i = 0; i < n; ++i) {
+            const int k = (ctx->tev_next + kTimingRing - 1 - i) % kTimingRing;
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ctx->tev[2 * k], ctx->tev[2 * k + 1]));
+            *sum_ms += (double)ms;
+        }
+        *n_evals = n;
+    }
+    if (reset) ctx->tev_pending = 0;
+    return BEATGPU_OK;
+}
+
+int beatgpu_stack_blocking(beatgpu_ctx* ctx, int wmap_id, int n_slipvars, int* chunk_patches, int* n_chunks,
+                           int64_t* chunk_bytes, int64_t* l2_bytes)
+{
+    GET_WMAP(wmap_id);
+    if (!w.axes_set) return fail(ctx, BEATGPU_E_NOTREADY, "stack_blocking: no GF library declared for wavemap %d", wmap_id);
+    if (n_slipvars < 1 || n_slipvars > BEATGPU_MAX_SLIPVARS) return fail(ctx, BEATGPU_E_ARG, "stack_blocking: n_slipvars %d", n_slipvars);
+    int chunk = 0, nchunk = 0;
+    int64_t cb = 0;
+    derive_chunk(ctx, w, n_slipvars, (int)w.dims[1], &chunk, &nchunk, &cb);
+    if (chunk_patches) *chunk_patches = chunk;
+    if (n_chunks) *n_chunks = nchunk;
+    if (chunk_bytes) *chunk_bytes = cb;
+    if (l2_bytes) *l2_bytes = (int64_t)ctx->prop.l2CacheSize;
+    return BEATGPU_OK;
+}
+
+#ifndef BEATGPU_SRC_HASH
+#define BEATGPU_SRC_HASH "unknown"
+#endif
+const char* beatgpu_source_hash(void) { return BEATGPU_SRC_HASH; }
 
 int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_bytes, int rows_per_warp, int n_launch,
                          float* ms_per_launch, double* bytes_per_launch)

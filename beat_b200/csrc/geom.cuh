@@ -276,7 +276,7 @@ struct GeomSumArgs {
     GeomStoreDev store;
     const RcvPlan* rplan;                      // [B, nr]
     const ChainPlan* cplan;                    // [B]
-    const unsigned char* chain_bad;            // [B]
+    unsigned char* chain_bad;                  // [B]; a CTA that loses a bulk copy marks its chain so the filter pass emits NaN
     const int* rcv_first;                      // [nr + 1] CSR into tgt_of
     const int* tgt_of;                         // target index of each channel of a receiver
     const float* tgt_f;                        // [nt, 3] sensor factors (north, east, down) = (ca*cd, sa*cd, sd) of azimuth/dip
@@ -287,7 +287,8 @@ struct GeomSumArgs {
     float* rawT;                               // [nt, n4, B, 4] raw traces, chain-interleaved
     double* mean;                              // [B, nt] mean of each raw trace
     int accumulate;                            // second and further sources: add to what the previous source left (heart.py:3719-3724)
-    unsigned int* err;                         // bulk-copy time-outs (must stay 0)
+    unsigned int* err;                         // [2]: bulk-copy time-outs of this call (err[0], cleared per call) and since the
+                                               // last beatgpu_geom_timeouts query (err[1]); both must stay 0
 };
 
 struct __align__(16) RowInfo {
@@ -320,7 +321,11 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
 
     const int tid = threadIdx.x;
     const int r = blockIdx.x / a.B, c = blockIdx.x % a.B;
-    if (a.chain_bad[c] || *(volatile unsigned int*)a.err) return;                 // uniform per CTA; after a time-out the grid drains
+    if (a.chain_bad[c]) return;                                                   // uniform per CTA
+    if (*(volatile unsigned int*)a.err) {                                         // after a time-out the grid drains: this chain gets no
+        if (tid == 0) a.chain_bad[c] = 1;                                         // raw trace, so it must not be filtered from stale scratch
+        return;
+    }
     const ChainPlan& cp = a.cplan[c];
     const RcvPlan& rp = a.rplan[(long)c * a.nr + r];
     const int n_stf = cp.n_stf;
@@ -437,7 +442,10 @@ __global__ void __launch_bounds__(kGeomThreads) gf_delay_sum_kernel(GeomSumArgs 
         }
         __syncthreads();
     }
-    if (__syncthreads_or(!ok)) { if (tid == 0) atomicAdd(a.err, 1u); return; }
+    if (__syncthreads_or(!ok)) {
+        if (tid == 0) { atomicAdd(a.err, 1u); atomicAdd(a.err + 1, 1u); a.chain_bad[c] = 1; }   // chain rejected (NaN), never stale data
+        return;
+    }
 
     // ---- per target channel of this receiver: sensor projection, STF convolution, mean, store.
     // The combined trace is laid out in slot 0 so that comb[n_stf - 1] is 16-byte aligned: a thread then produces four

@@ -103,6 +103,11 @@ _SIGNATURES = {
     "beatgpu_index_violations": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_launch_count": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_last_stack_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "beatgpu_stack_ms_accum": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "beatgpu_stack_blocking": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_int64)]),
+    "beatgpu_source_hash": (C.c_char_p, []),
+    "beatgpu_geom_timeouts": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_geom_set_source": (C.c_int, [_P, C.POINTER(GeomLayout), _P, C.c_double, C.c_double, C.c_double]),
     "beatgpu_geom_upload_store": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                                             C.POINTER(C.c_int)]),
@@ -138,6 +143,11 @@ def load():
     return _lib
 
 
+def source_hash():
+    """Hash of the sources the loaded libbeatgpu.so was built from (beatgpu_source_hash)."""
+    return load().beatgpu_source_hash().decode()
+
+
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -149,8 +159,11 @@ def _f64(a, shape=None):
     return a
 
 
-def _i32(a):
-    return np.ascontiguousarray(a, dtype=np.int32)
+def _i32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    if shape is not None and tuple(a.shape) != tuple(shape):
+        raise ValueError("expected shape %s, got %s" % (tuple(shape), a.shape))
+    return a
 
 
 def _check_q(q, n_params, what):
@@ -171,6 +184,14 @@ class Context:
             raise BeatGpuError(rc, self._lib.beatgpu_last_error(None).decode())
         self._h = h
         self.device = int(device)
+        # sizes the C entries trust (they read nt*ns, nt*ns*ns, canon_len ... elements from raw pointers): every array
+        # is checked against them here before its pointer crosses the ABI
+        self._np_total = self._nsf = None
+        self._canon_len = None
+        self._n_hypers = 0
+        self._n_slipvars = None
+        self._wm = {}               # wavemap id -> (nt, ns)
+        self._geo = None            # (nobs, [n_i per dataset])
 
     def close(self):
         if getattr(self, "_h", None):
@@ -219,21 +240,36 @@ class Context:
     # ------------------------------------------------------------------ operands
     def set_fault(self, n_patch_dip, n_patch_strike, patch_size):
         nd, ns, ps = _i32(n_patch_dip), _i32(n_patch_strike), _f64(patch_size)
+        if nd.ndim != 1 or ns.shape != nd.shape or ps.shape != nd.shape:
+            raise ValueError("set_fault: n_patch_dip, n_patch_strike and patch_size must be 1-d arrays of one length")
         self._check(self._lib.beatgpu_set_fault(self._h, len(nd), _ptr(nd), _ptr(ns), _ptr(ps)))
+        self._nsf = len(nd)
+        self._np_total = int((nd.astype(np.int64) * ns).sum())
 
     def set_layout(self, layout: Layout, fixed=None):
-        fx = None if fixed is None else _f64(fixed)
+        if self._np_total is None:
+            raise BeatGpuError(E_NOTREADY, "set_layout: call set_fault first")
+        canon = (layout.n_slipvars + 2) * self._np_total + 3 * self._nsf + layout.n_hypers + layout.n_time_shifts
+        fx = None if fixed is None else _f64(fixed, (canon,))      # the C side copies canon_len doubles
         self._check(self._lib.beatgpu_set_layout(self._h, C.byref(layout), _ptr(fx)))
         self._n_params = layout.n_params
+        self._canon_len, self._n_hypers, self._n_slipvars = canon, layout.n_hypers, layout.n_slipvars
 
     def add_wavemap(self, n_targets, n_samples, interpolation, station_idx, hyper_idx, nsamples):
-        st = None if station_idx is None else _i32(station_idx)
-        hi, nsm = _i32(hyper_idx), _i32(nsamples)
+        nt = int(n_targets)
+        st = None if station_idx is None else _i32(station_idx, (nt,))
+        hi, nsm = _i32(hyper_idx, (nt,)), _i32(nsamples, (nt,))
         wid = C.c_int()
         self._check(self._lib.beatgpu_add_wavemap(self._h, int(n_targets), int(n_samples),
                                                   INTERPOLATION.get(interpolation, interpolation),
                                                   _ptr(st), _ptr(hi), _ptr(nsm), C.byref(wid)))
+        self._wm[wid.value] = (nt, int(n_samples))
         return wid.value
+
+    def _wm_shape(self, wmap, what):
+        if wmap not in self._wm:
+            raise ValueError("%s: unknown wavemap id %r" % (what, wmap))
+        return self._wm[wmap]
 
     def upload_gflib(self, wmap, slipvar, traces, store_dtype, dur_min, dur_step, st_min, st_step):
         if traces.dtype == np.float64:
@@ -244,6 +280,9 @@ class Context:
             raise GFLibraryError("GF library dtype %s not supported" % traces.dtype)
         if traces.ndim != 5 or not traces.flags["C_CONTIGUOUS"]:
             raise GFLibraryError("GF library must be a C-contiguous 5-d array (targets, patches, durations, starttimes, samples)")
+        nt, ns = self._wm_shape(wmap, "upload_gflib")
+        if traces.shape[0] != nt or traces.shape[4] != ns:
+            raise GFLibraryError("GF library is %s, wavemap %d has %d targets x %d samples" % (traces.shape, wmap, nt, ns))
         dims = np.asarray(traces.shape, dtype=np.int64)
         self._check(self._lib.beatgpu_upload_gflib(self._h, wmap, slipvar, traces.ctypes.data_as(C.c_void_p), src,
                                                    store_dtype, _ptr(dims), dur_min, dur_step, st_min, st_step))
@@ -256,7 +295,7 @@ class Context:
         return p.value, ld.value
 
     def upload_data(self, wmap, data):
-        d = _f64(data)
+        d = _f64(data, self._wm_shape(wmap, "upload_data"))
         self._check(self._lib.beatgpu_upload_data(self._h, wmap, _ptr(d)))
 
     def update_weights_dev(self, wmap, U_dev_ptr, slog_pdet_dev_ptr, band_rtol=-1.0):
@@ -265,28 +304,49 @@ class Context:
                                                          band_rtol))
 
     def update_weights(self, wmap, U, slog_pdet, band_rtol=-1.0):
-        U, lp = _f64(U), _f64(slog_pdet)
+        nt, ns = self._wm_shape(wmap, "update_weights")
+        U, lp = _f64(U, (nt, ns, ns)), _f64(slog_pdet, (nt,))
         self._check(self._lib.beatgpu_update_weights(self._h, wmap, _ptr(U), _ptr(lp), band_rtol))
 
     def set_geodetic(self, slices, G_list, data, odw, U_list, slog_pdet, nsamples, hyper_idx):
+        if self._n_slipvars is None:
+            raise BeatGpuError(E_NOTREADY, "set_geodetic: call set_fault and set_layout first")
         lo = _i32([s[0] for s in slices])
         hi = _i32([s[1] for s in slices])
-        Gs = [_f64(g) for g in G_list]
+        nds = len(slices)
+        data = _f64(data)
+        if data.ndim != 1:
+            raise ValueError("set_geodetic: data must be the concatenated observation vector [nobs]")
+        nobs = data.shape[0]
+        odw = _f64(odw, (nobs,))
+        if len(G_list) != self._n_slipvars:
+            raise ValueError("set_geodetic: %d libraries for %d slip variables" % (len(G_list), self._n_slipvars))
+        Gs = [_f64(g, (self._np_total, nobs)) for g in G_list]
         arr = (C.c_void_p * len(Gs))(*[g.ctypes.data for g in Gs])
-        data, odw = _f64(data), _f64(odw)
-        Ucat = np.concatenate([_f64(u).ravel() for u in U_list])
-        lp, nsm, hix = _f64(slog_pdet), _i32(nsamples), _i32(hyper_idx)
+        if len(U_list) != nds:
+            raise ValueError("set_geodetic: %d weight matrices for %d datasets" % (len(U_list), nds))
+        sizes = [int(h - l) for l, h in zip(lo, hi)]
+        Ucat = np.concatenate([_f64(u, (n, n)).ravel() for u, n in zip(U_list, sizes)])
+        lp, nsm, hix = _f64(slog_pdet, (nds,)), _i32(nsamples, (nds,)), _i32(hyper_idx, (nds,))
+        self._geo = (nobs, sizes)
         self._check(self._lib.beatgpu_set_geodetic(self._h, len(data), len(slices), _ptr(lo), _ptr(hi),
                                                    C.cast(arr, C.c_void_p), _ptr(data), _ptr(odw), _ptr(Ucat), _ptr(lp),
                                                    _ptr(nsm), _ptr(hix)))
 
     def update_geodetic_weights(self, U_list, slog_pdet):
-        Ucat = np.concatenate([_f64(u).ravel() for u in U_list])
-        lp = _f64(slog_pdet)
+        if self._geo is None:
+            raise BeatGpuError(E_NOTREADY, "update_geodetic_weights: geodetic composite not set")
+        sizes = self._geo[1]
+        if len(U_list) != len(sizes):
+            raise ValueError("update_geodetic_weights: %d weight matrices for %d datasets" % (len(U_list), len(sizes)))
+        Ucat = np.concatenate([_f64(u, (n, n)).ravel() for u, n in zip(U_list, sizes)])
+        lp = _f64(slog_pdet, (len(sizes),))
         self._check(self._lib.beatgpu_update_geodetic_weights(self._h, _ptr(Ucat), _ptr(lp)))
 
     def set_laplacian(self, L, sdet, hyper_idx):
-        L = _f64(L)
+        if self._np_total is None:
+            raise BeatGpuError(E_NOTREADY, "set_laplacian: call set_fault and set_layout first")
+        L = _f64(L, (self._np_total, self._np_total))
         self._check(self._lib.beatgpu_set_laplacian(self._h, _ptr(L), float(sdet), int(hyper_idx)))
 
     def n_outputs(self):
@@ -310,9 +370,13 @@ class Context:
 
     def stack_batch(self, wmap, durations, starttimes, slips, nt, ns):
         d, st, sl = _f64(durations), _f64(starttimes), _f64(slips)
+        if (nt, ns) != self._wm_shape(wmap, "stack_batch"):
+            raise ValueError("stack_batch: wavemap %d is %s, not (%d, %d)" % (wmap, self._wm[wmap], nt, ns))
+        if d.ndim != 2 or sl.ndim != 3:
+            raise ValueError("stack_batch: durations [B, np], starttimes [B, nt, np], slips [nvar, B, np]")
         B, npatch = d.shape
         nvar = sl.shape[0]
-        if st.shape != (B, nt, npatch) or sl.shape != (nvar, B, npatch):
+        if st.shape != (B, nt, npatch) or sl.shape != (nvar, B, npatch) or (self._np_total is not None and npatch != self._np_total):
             raise ValueError("stack_batch: inconsistent shapes")
         out = np.empty((B, nt, ns))
         self._check(self._lib.beatgpu_stack_batch(self._h, wmap, B, nvar, _ptr(d), _ptr(st), _ptr(sl), _ptr(out)))
@@ -320,6 +384,8 @@ class Context:
 
     def misfit_batch(self, wmap, residuals, hypers):
         r, h = _f64(residuals), _f64(hypers)
+        if r.ndim != 3 or r.shape[1:] != self._wm_shape(wmap, "misfit_batch"):
+            raise ValueError("misfit_batch: residuals must be [B, %d, %d], got %s" % (self._wm[wmap] + (r.shape,)))
         B, nt, _ = r.shape
         if h.ndim != 2 or h.shape[0] != B:
             raise ValueError("hypers must be [B, n_hypers]")
@@ -378,6 +444,24 @@ class Context:
         ms = C.c_float()
         self._check(self._lib.beatgpu_last_stack_ms(self._h, C.byref(ms)))
         return ms.value
+
+    def stack_ms_accum(self, reset=True):
+        """(sum of the stack + misfit kernel durations [ms], evaluations covered) since the last reset."""
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self._lib.beatgpu_stack_ms_accum(self._h, 1 if reset else 0, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def stack_blocking(self, wmap, n_slipvars=None):
+        """L2 blocking of the stacking pass: dict(chunk_patches, n_chunks, chunk_bytes, l2_bytes)."""
+        c, n, cb, l2 = C.c_int(), C.c_int(), C.c_int64(), C.c_int64()
+        nv = int(n_slipvars if n_slipvars is not None else (self._n_slipvars or 1))
+        self._check(self._lib.beatgpu_stack_blocking(self._h, wmap, nv, C.byref(c), C.byref(n), C.byref(cb), C.byref(l2)))
+        return dict(chunk_patches=c.value, n_chunks=n.value, chunk_bytes=cb.value, l2_bytes=l2.value)
+
+    def geom_timeouts(self):
+        n = C.c_int64()
+        self._check(self._lib.beatgpu_geom_timeouts(self._h, C.byref(n)))
+        return n.value
 
     def probe_gather(self, mode, ws_bytes, row_bytes=480, rows_per_warp=4096, n_launch=3):
         """Diagnostics: measured row-gather bandwidth [GB/s] (mode 0 LDG.128, 1 TMA + smem read, 2 TMA only)."""

@@ -232,6 +232,24 @@ int beatgpu_launch_count(beatgpu_ctx* ctx, int64_t* n_launches);
  * with CUDA events: milliseconds of the last loglike batch's stack kernel(s).                */
 int beatgpu_last_stack_ms(beatgpu_ctx* ctx, float* ms);
 
+/* Sum of the CUDA-event durations [ms] of the dominant kernels (gf stack + misfit pass) of the fused evaluations
+ * enqueued since the last reset, and how many evaluations that covers (at most the last 1024).  The event pairs are
+ * recorded inside every beatgpu_ffi_loglike_batch[_dev] call on the ctx stream, so a caller can time a whole loop
+ * and learn the kernels' share of it afterwards (bench.py: roofline.kernel_ms is measured INSIDE the timed region).
+ * Synchronises on the last recorded event.  reset != 0 clears the accumulator after reading.                  */
+int beatgpu_stack_ms_accum(beatgpu_ctx* ctx, int reset, double* sum_ms, int64_t* n_evals);
+
+/* How the stacking pass of a wavemap is blocked for the L2 cache: patches per chunk, number of chunks, the library
+ * bytes one chunk spans (chunk * n_slipvars * ndurations * nstarttimes * row bytes) and the device's L2 size.  The
+ * chunk is derived from cudaDeviceProp.l2CacheSize (working set <= 40 % of L2; BEATGPU_L2_FRAC / BEATGPU_CHUNK
+ * override) so that libraries with larger per-patch blocks keep the all-chains-stream-through-L2 behaviour.   */
+int beatgpu_stack_blocking(beatgpu_ctx* ctx, int wmap_id, int n_slipvars, int* chunk_patches, int* n_chunks,
+                           int64_t* chunk_bytes, int64_t* l2_bytes);
+
+/* Hash of the CUDA / C++ sources this library was built from (build.py passes it to nvcc): lets a committed ncu
+ * traffic record be matched against the build that is actually running.                                      */
+const char* beatgpu_source_hash(void);
+
 /* ---------------------------------------------------------------- geometry mode -------------
  * The point-source ("geometry") seismic composite of BASELINE config 2: per chain a double-couple source
  * (east_shift, north_shift, depth [km], strike, dip, rake [deg], magnitude, time [s], STF duration [s]) is turned into
@@ -301,6 +319,11 @@ int beatgpu_geom_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q_dev,
 
 /* Forward model only: heart.seis_synthetics(..., outmode="array") for B chains: synthetics [B, nt, ns].        */
 int beatgpu_geom_synthetics_batch(beatgpu_ctx* ctx, int wmap_id, int B, const double* q, double* synthetics);
+
+/* GF-store bulk copies that timed out in beatgpu_geom_loglike_batch_dev calls since the last query (the host-pointer
+ * entries report theirs as BEATGPU_E_CUDA).  The chains concerned already carry NaN logpts (rejected by a sampler);
+ * a non-zero count means the device lost copies.  Reads and resets the counter; synchronises.                  */
+int beatgpu_geom_timeouts(beatgpu_ctx* ctx, int64_t* count);
 
 /* Diagnostics (not on the product path): measured ceiling of the access pattern the GF stacking uses.  Gathers
  * pseudo-random rows of row_bytes (multiple of 16, <= 16384) from a zero-filled working set of ws_bytes with
