@@ -1551,9 +1551,10 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
                          float* ms_per_launch, double* bytes_per_launch)
 {
     if (!ctx || !ms_per_launch || !bytes_per_launch) return BEATGPU_E_ARG;
-    if (mode < 0 || mode > 2 || row_bytes < 16 || row_bytes > kProbeMaxRow || row_bytes % 16 || ws_bytes < row_bytes ||
+    if (mode < 0 || mode > 8 || row_bytes < 16 || row_bytes > kProbeMaxRow || row_bytes % 16 || ws_bytes < row_bytes ||
         rows_per_warp < 1 || n_launch < 1)
-        return fail(ctx, BEATGPU_E_ARG, "probe_gather: bad arguments (row_bytes: multiple of 16, <= %d)", kProbeMaxRow);
+        return fail(ctx, BEATGPU_E_ARG, "probe_gather: bad arguments (mode 0..8; row_bytes: multiple of 16, <= %d)", kProbeMaxRow);
+    CK(cudaSetDevice(ctx->device));
     ProbeArgs a;
     memset(&a, 0, sizeof(a));
     a.row_bytes = row_bytes;
@@ -1563,18 +1564,22 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
     if (a.n_rows > 0x40000000L) return fail(ctx, BEATGPU_E_ARG, "probe_gather: working set too large");
     a.row_mask = (uint32_t)(a.n_rows - 1);
     a.rows_per_warp = rows_per_warp;
+    const bool smem_only = mode >= 5;                              // rows live in (distributed) shared memory: no working set
     unsigned char* d_ws = nullptr;
     float* d_sink = nullptr;
-    CK(cudaMalloc((void**)&d_ws, (size_t)a.n_rows * row_bytes));
+    if (!smem_only) {
+        CK(cudaMalloc((void**)&d_ws, (size_t)a.n_rows * row_bytes));
+        CK(cudaMemsetAsync(d_ws, 0, (size_t)a.n_rows * row_bytes, ctx->stream));
+    }
     CK(cudaMalloc((void**)&d_sink, 8));
-    CK(cudaMemsetAsync(d_ws, 0, (size_t)a.n_rows * row_bytes, ctx->stream));
     CK(cudaMemsetAsync(d_sink, 0, 8, ctx->stream));
     a.ws = d_ws; a.sink = d_sink; a.err = (unsigned int*)(d_sink + 1);
-    // LDG mode: 16 CTAs x 4 warps = all 64 warp slots of every SM.  TMA modes: ring of `depth` rows per warp in
-    // dynamic shared memory, as many CTAs per SM as ~200 KB of rings allow.
-    int per_sm = 16;
+    // LDG mode: 16 CTAs x 4 warps = all 64 warp slots of every SM.  TMA modes: ring of `depth` rows (modes 1, 2) or of
+    // kBatchRing batches of kBatchRows rows (modes 3, 4) per warp in dynamic shared memory, as many CTAs per SM as ~200 KB
+    // of rings allow.  Shared-memory modes (5..8): 32 KB of rows per CTA, cluster of 1 / 2 / 4 / 8 CTAs.
+    int per_sm = 16, cluster = 1, rows_smem = 0;
     size_t smem = 0;
-    if (mode != 0) {
+    if (mode == 1 || mode == 2) {
         a.depth = (int)std::max<size_t>(1, std::min<size_t>(kProbeDepth, (size_t)(48 * 1024) / ((size_t)kProbeWarps * row_bytes)));
         smem = (size_t)kProbeWarps * a.depth * row_bytes + (size_t)kProbeWarps * a.depth * sizeof(uint64_t);
         per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(200 * 1024) / (smem + 1024)));
@@ -1582,8 +1587,25 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
             CK(cudaFuncSetAttribute(probe_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute(probe_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
+    } else if (mode == 3 || mode == 4) {
+        smem = (size_t)kProbeWarps * kBatchRing * kBatchRows * row_bytes + (size_t)kProbeWarps * kBatchRing * sizeof(uint64_t);
+        if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin) {
+            cudaFree(d_ws); cudaFree(d_sink);
+            return fail(ctx, BEATGPU_E_ARG, "probe_gather: batched bulk-copy ring of %zu B exceeds shared memory (row_bytes too large)", smem);
+        }
+        per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(216 * 1024) / (smem + 1024)));
+        CK(cudaFuncSetAttribute(probe_tma_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(probe_tma_batch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        a.rows_per_warp = std::max(kBatchRows, rows_per_warp / kBatchRows * kBatchRows);
+    } else if (smem_only) {
+        cluster = 1 << (mode - 5);
+        rows_smem = std::max(1, (32 * 1024) / row_bytes);
+        smem = (size_t)rows_smem * row_bytes;
+        per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(216 * 1024) / (smem + 1024)));
+        CK(cudaFuncSetAttribute(probe_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int grid = ctx->prop.multiProcessorCount * per_sm;
+    int grid = ctx->prop.multiProcessorCount * per_sm;
+    grid -= grid % cluster;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -1591,7 +1613,19 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
         if (i == 1) CK(cudaEventRecord(e0, ctx->stream));
         if (mode == 0) probe_ldg_kernel<<<grid, kProbeThreads, 0, ctx->stream>>>(a);
         else if (mode == 1) probe_tma_kernel<true><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
-        else probe_tma_kernel<false><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
+        else if (mode == 2) probe_tma_kernel<false><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
+        else if (mode == 3) probe_tma_batch_kernel<true><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
+        else if (mode == 4) probe_tma_batch_kernel<false><<<grid, kProbeThreads, smem, ctx->stream>>>(a);
+        else {
+            cudaLaunchConfig_t cfg;
+            memset(&cfg, 0, sizeof(cfg));
+            cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kProbeThreads); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, probe_dsmem_kernel, a, rows_smem, cluster));
+        }
         CKL();
     }
     CK(cudaEventRecord(e1, ctx->stream));
@@ -1604,7 +1638,7 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
     cudaFree(d_ws); cudaFree(d_sink);
     if (err) return fail(ctx, BEATGPU_E_CUDA, "probe_gather: %u warps timed out waiting for a bulk copy", err);
     *ms_per_launch = ms / n_launch;
-    *bytes_per_launch = (double)grid * kProbeWarps * (double)rows_per_warp * row_bytes;
+    *bytes_per_launch = (double)grid * kProbeWarps * (double)a.rows_per_warp * row_bytes;
     return BEATGPU_OK;
 }
 

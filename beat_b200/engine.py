@@ -147,6 +147,11 @@ class BatchedFFILogLike:
         self.ctx.ffi_loglike_batch_dev(B, q_dev.data_ptr(), logpts_out.data_ptr(), like_out.data_ptr())
         return logpts_out, like_out
 
+    def drain_diagnostics(self):
+        """Counters of the device-pointer path since the last call (read + reset; one host sync): library taps that fell
+        outside the library (the chains concerned carry NaN logpts and are rejected by the sampler)."""
+        return {"index_violations": self.ctx.index_violations()}
+
     def get_synthetics(self, Q, wmap_index=0):
         """Forward model only (reference: SeismicDistributerComposite.get_synthetics, outmode="array",
         beat/models/seismic.py:1351-1507): Q [B, n_params] or [n_params] -> synthetics [B, nt, ns] / [nt, ns]."""

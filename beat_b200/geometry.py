@@ -207,6 +207,11 @@ class BatchedGeometryLogLike:
         self.ctx.geom_loglike_batch_dev(B, q_dev.data_ptr(), logpts_out.data_ptr(), like_out.data_ptr())
         return logpts_out, like_out
 
+    def drain_diagnostics(self):
+        """Counters of the device-pointer path since the last call (read + reset; one host sync): proposals whose source
+        left the GF store (their logpts are NaN, i.e. rejected) and GF-store bulk copies that timed out (must be 0)."""
+        return {"index_violations": self.ctx.index_violations(), "geom_timeouts": self.ctx.geom_timeouts()}
+
     def get_synthetics(self, Q, wmap_index=0):
         """heart.seis_synthetics(..., outmode="array") for every chain: [B, nt, ns] (or [nt, ns] for one point)."""
         Q = np.ascontiguousarray(Q, dtype=np.float64)

@@ -464,7 +464,9 @@ class Context:
         return n.value
 
     def probe_gather(self, mode, ws_bytes, row_bytes=480, rows_per_warp=4096, n_launch=3):
-        """Diagnostics: measured row-gather bandwidth [GB/s] (mode 0 LDG.128, 1 TMA + smem read, 2 TMA only)."""
+        """Diagnostics: measured row-gather bandwidth [GB/s].  mode 0 LDG.128, 1 TMA per row + smem read, 2 TMA per row only,
+        3 / 4 batched TMA (16 rows per mbarrier) with / without smem read, 5 rows from local shared memory, 6 / 7 / 8 rows
+        from the shared memory of a 2 / 4 / 8-CTA cluster (DSMEM)."""
         ms, nbytes = C.c_float(), C.c_double()
         self._check(self._lib.beatgpu_probe_gather(self._h, mode, int(ws_bytes), row_bytes, rows_per_warp, n_launch,
                                                    C.byref(ms), C.byref(nbytes)))

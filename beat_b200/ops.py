@@ -212,12 +212,23 @@ def multivariate_normal_chol(datasets, weights, hyperparams, residuals, hp_speci
     for i, ds in enumerate(datasets):
         name = "_".join(("h", ds.typ))                                  # distributions.py:24-25
         hp = np.asarray(hyperparams[name], dtype=np.float64)
-        if hp_specific:
+        if hp_specific:                                                # one entry per dataset of that type (:123-126)
             k = counts.get(name, 0)
             counts[name] = k + 1
             H[:, i] = hp[..., k]
+        elif hp.ndim == 0 or hp.size == 1:                             # one value for all chains and datasets
+            H[:, i] = hp.reshape(())
+        elif hp.ndim == 1 and hp.shape[0] == B and B != n_t:           # [B]: per chain
+            H[:, i] = hp
+        elif hp.ndim == 1 and hp.shape[0] == n_t and B != n_t:         # [n_t]: per dataset
+            H[:, i] = hp[i]
+        elif hp.ndim == 2 and hp.shape == (B, n_t):                    # [B, n_t]
+            H[:, i] = hp[:, i]
+        elif hp.ndim == 2 and hp.shape == (B, 1):
+            H[:, i] = hp[:, 0]
         else:
-            H[:, i] = hp if hp.ndim == 0 else hp.reshape(-1)
+            raise ValueError("hyperparameter %s: shape %s is ambiguous or does not match B=%d chains / n_t=%d datasets "
+                             "(pass a scalar, [B, 1] or [B, n_t])" % (name, hp.shape, B, n_t))
     ctx = Context(device)
     try:
         wid = ctx.add_wavemap(n_t, ns, "nearest_neighbor", None, np.arange(n_t, dtype=np.int32),

@@ -28,6 +28,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from .covariance import ensure_cov_psd        # the one faithful restatement of beat/utility.py:1034-1056 (+ repair_covariance)
+
 
 def tune_scale(scale, acc_rate):
     """pymc's Metropolis ``tune`` rule, used by the reference as ``step_tune`` (metropolis.py:300-302), vectorised.
@@ -61,15 +63,16 @@ def calc_beta(likelihoods, beta, coef_variation=1.0):
     return current_beta, old_beta, temp / np.sum(temp)
 
 
-def ensure_cov_psd(cov):
-    """beat/utility.py:1034-1056: symmetrise / repair a covariance that is not positive definite."""
+def proposal_factor(cov):
+    """A factor F with F F^T = cov for the MultivariateNormal proposal (sampler/base.py:163-167 draws with
+    numpy's SVD-based ``multivariate_normal``, which accepts a semi-definite covariance): Cholesky when it exists,
+    else the symmetric eigen-factor of the repaired matrix -- same distribution either way."""
+    cov = ensure_cov_psd(np.atleast_2d(cov))
     try:
-        np.linalg.cholesky(cov)
-        return cov
+        return np.linalg.cholesky(cov)
     except np.linalg.LinAlgError:
         w, v = np.linalg.eigh((cov + cov.T) / 2.0)
-        w = np.clip(w, 1e-12 * max(1.0, w.max()), None)
-        return (v * w).dot(v.T)
+        return v * np.sqrt(np.clip(w, 0.0, None))
 
 
 def calc_covariance(array_population, weights):
@@ -104,6 +107,7 @@ class BatchedMetropolis:
         self.upper = torch.as_tensor(np.asarray(upper, dtype=np.float64), device=self.device)
         self.n_chains = n_chains
         self.n_params = self.lower.numel()
+        self.scale0 = float(scale)
         self.scaling = torch.full((n_chains,), float(scale), dtype=torch.float64, device=self.device)
         self.tune, self.tune_interval = tune, tune_interval
         self.steps_until_tune = tune_interval
@@ -118,10 +122,17 @@ class BatchedMetropolis:
     def n_evals(self):
         return int(self._n_evals.item())
 
+    def start_stage(self):
+        """Every chain of a stage starts from the PARENT step object's state: the reference pickles ``step`` into each
+        forked chain (sampler/base.py:260-313), so per-chain tuning of the previous stage is never carried over --
+        scaling back to the constructor's value, tuning counters cleared (metropolis.py:97-106)."""
+        self.scaling.fill_(self.scale0)
+        self.steps_until_tune = self.tune_interval
+        self.accepted.zero_()
+
     def set_proposal_covariance(self, cov):
         """MultivariateNormal proposal (sampler/base.py:163-167): draws = z @ chol(cov).T."""
-        L = np.linalg.cholesky(ensure_cov_psd(np.atleast_2d(cov)))
-        self.chol = self.torch.as_tensor(L, device=self.device)
+        self.chol = self.torch.as_tensor(proposal_factor(cov), device=self.device)
 
     def initial_llk(self, q):
         """Stage 0: evaluate the start population; non-finite llk raises (metropolis.py:277-284)."""
@@ -155,6 +166,14 @@ class BatchedMetropolis:
         self.accepted += accept.to(torch.float64)
         self.steps_until_tune -= 1
         return q_new, logpts_new, like_new, accept
+
+
+def _drain_diagnostics(evaluator):
+    """Per-stage read-out of the evaluator's device-side counters (``drain_diagnostics`` of the object a bound
+    ``eval_device`` belongs to); plain callables (tests, toy posteriors) have none."""
+    owner = getattr(evaluator, "__self__", None)
+    fn = getattr(owner, "drain_diagnostics", None) or getattr(evaluator, "drain_diagnostics", None)
+    return fn() if fn is not None else {}
 
 
 def _checkpoint_path(checkpoint_dir, stage):
@@ -276,8 +295,7 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         like = torch.as_tensor(like_all, device=device)[sel].contiguous()
         logpts = logpts_all[sel].contiguous()
         draws = n_steps * (sample_factor_final_stage if final else 1)
-        mh.steps_until_tune = mh.tune_interval
-        mh.accepted.zero_()
+        mh.start_stage()
         n_acc = torch.zeros((), dtype=torch.float64, device=device)
         for istep in range(draws):
             q, logpts, like, acc = mh.step(q, logpts, like)
@@ -285,6 +303,12 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
             if on_step is not None:
                 on_step(stage + 1, istep, q, logpts, like)
         acc_hist.append(float(n_acc.item()) / max(1, draws))
+        diag = _drain_diagnostics(evaluator)                   # once per stage: the device-pointer path never syncs
+        if diag.get("geom_timeouts"):
+            raise RuntimeError("stage %d: %d GF-store bulk copies timed out on the device (affected chains were rejected "
+                               "with NaN); stopping" % (stage + 1, diag["geom_timeouts"]))
+        if log and diag.get("index_violations"):
+            log("stage %d: %d library / grid indices out of range (those proposals were rejected)" % (stage + 1, diag["index_violations"]))
         beta = new_beta
         betas.append(beta)
         stage += 1

@@ -116,6 +116,7 @@ def workload_config(args, n_gpus, chains):
         "chains_per_gpu": chains, "global_chains": chains * n_gpus, "parallelism": "chains sharded x%d" % n_gpus,
         "gf_storage": args.store, "interpolation": args.interpolation,
         "accumulate": ("f32 FMA per patch pair, f64 running sum" if args.store == "f32" else "f64 FMA") + "; sweep, residual, misfit in f64",
+        "scaling_protocol": "weak: chains_per_gpu fixed, one all-gather of llk per step; the `strong` block of the line holds n_chains = %d partitioned over the ranks" % chains,
         "l2": "inputs>L2 (GF library %.1f GB per GPU; q rotates between steps)" % (lib_bytes(a, args.store) / 1e9),
     }
 
@@ -241,12 +242,14 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args, args.gpus, per_step), gf_storage="f64 (host)"),
+        # the GPU arm's own config (same workload); what the CPU actually ran per step is in cpu_baseline.sample
+        "config": workload_config(args, args.gpus, args.chains),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d chains per step (bounded sample of the 4000-chain workload), same C3 shapes with 2 "
-                                   "duration nodes in the host library; %s fast_sweep + numpy stack_all + numpy llk, one "
+                         "sample": "%d chains per step (bounded sample of the %d-chain workload), same C3 shapes, f64 host "
+                                   "library with 2 of the 17 duration nodes (bounded RAM / build time; bytes gathered per "
+                                   "evaluation are identical); %s fast_sweep + numpy stack_all + numpy llk, one "
                                    "chain per call, fork pool over %d of %d cores (best of %s)"
-                                   % (per_step, "reference's compiled" if have_ref else "C-restated", cores, all_cores, cands)},
+                                   % (per_step, args.chains, "reference's compiled" if have_ref else "C-restated", cores, all_cores, cands)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -373,6 +376,34 @@ def run_gpu_arm(args):
         print(json.dumps(line), flush=True)
 
 
+DTYPE_LABEL = {"f32": "f32 library storage, f32 FMA per patch pair, f64 running sum; sweep, residual, misfit in f64",
+               "f64": "f64 (library storage and every operation)"}
+
+
+def touched_library_bytes(prob, a, store, interpolation, Q, t0):
+    """Distinct library bytes the chains `Q` (rupture onset times `t0` [B, np] from the device) gather in one step:
+    the HBM traffic an L2-perfect gather needs.  Same cells for every target (no station corrections in this workload)."""
+    wm = prob["wavemaps"][0]
+    off = prob["offsets"]
+    npatch = prob["npatches"]
+    dur = Q[:, off["durations"]:off["durations"] + npatch]
+    x = (dur - wm["dur_min"]) / wm["dur_step"]
+    y = (t0 - wm["st_min"]) / wm["st_step"]
+    nst = wm["nst"]
+    total_rows = 0
+    for p in range(npatch):
+        if interpolation == "multilinear":
+            dc, sc = np.ceil(x[:, p]).astype(np.int64), np.ceil(y[:, p]).astype(np.int64)
+            dfl = np.where(dc - x[:, p] == 0.0, dc, dc - 1)
+            sfl = np.where(sc - y[:, p] == 0.0, sc, sc - 1)
+            rows = np.concatenate([dc * nst + sc, dc * nst + sfl, dfl * nst + sc, dfl * nst + sfl])
+        else:
+            rows = np.rint(x[:, p]).astype(np.int64) * nst + np.rint(y[:, p]).astype(np.int64)
+        total_rows += np.unique(rows).size
+    row_bytes = a["ns"] * (4 if store == "f32" else 8)
+    return int(total_rows) * a["nt"] * len(prob["slip_vars"]) * row_bytes
+
+
 def _run_gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -392,6 +423,7 @@ def _run_gpu_arm(args):
 
     import torch
     import torch.distributed as dist
+    from beat_b200 import lib as beatlib
     from beat_b200 import synthetic
     from beat_b200.devlib import fill_library_on_device
     from beat_b200.engine import BatchedFFILogLike
@@ -408,104 +440,140 @@ def _run_gpu_arm(args):
     a = c3_args(args.quick)
     B = args.chains
     prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, build_library=False, noise=args.noise, **a)
-    ev = BatchedFFILogLike.from_problem(prob, device=local_rank, store_dtype="float32" if args.store == "f32" else "float64",
-                                        upload_libraries=False)
-    log("filling %.1f GB of synthetic GF library in HBM" % (lib_bytes(a, args.store) / 1e9))
-    fill_library_on_device(ev, prob, torch, device, args.store)
-    log("library ready")
-
     n_rot = 3
     Qs = [synthetic.draw_chains(prob, B, seed=4321 + 17 * rank + 1000 * r) for r in range(n_rot)]
-    q_dev = [torch.from_numpy(q).to(device) for q in Qs]
     q_pin = [torch.from_numpy(q).pin_memory() for q in Qs]
-    n_out = ev.n_out
-    logpts_dev = torch.empty((B, n_out), dtype=torch.float64, device=device)
-    like_dev = torch.empty((B,), dtype=torch.float64, device=device)
-    like_all = torch.empty((n_gpus * B,), dtype=torch.float64, device=device) if n_gpus > 1 else None
-    logpts_pin = torch.empty((B, n_out), dtype=torch.float64).pin_memory()
-    like_pin = torch.empty((B,), dtype=torch.float64).pin_memory()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def barrier():
         if n_gpus > 1:
             dist.barrier()
         torch.cuda.synchronize(device)
 
-    def step_resident(i):
-        ev.eval_device(q_dev[i % n_rot], logpts_dev, like_dev)
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=device)
         if n_gpus > 1:
-            dist.all_gather_into_tensor(like_all, like_dev)      # the per-stage exchange of SMC (llk of every chain)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    def step_e2e(i):
-        ev.eval_pinned(B, q_pin[i % n_rot].data_ptr(), logpts_pin.data_ptr(), like_pin.data_ptr())
-        if n_gpus > 1:
-            like_dev.copy_(like_pin, non_blocking=True)
+    def make_evaluator(store):
+        ev = BatchedFFILogLike.from_problem(prob, device=local_rank, store_dtype="float32" if store == "f32" else "float64",
+                                            upload_libraries=False)
+        log("filling %.1f GB of synthetic GF library (%s) in HBM" % (lib_bytes(a, store) / 1e9, store))
+        fill_library_on_device(ev, prob, torch, device, store)
+        return ev
+
+    def measure(ev, store, nchains, steps, warmup, gather_every_step, with_clocks=False, with_e2e=True):
+        """K timed lock-step evaluations of `nchains` chains per rank: resident (`value`) and through the host-pointer
+        entry (`e2e`).  The stack + misfit kernel time is summed from the event pairs the library records INSIDE the
+        timed loop.  N > 1: one all-gather of the per-chain llk -- every step (the round-1 protocol) or once at the end
+        of the K steps (the SMC stage boundary, timed separately)."""
+        n_out = ev.n_out
+        q_dev = [torch.from_numpy(q[:nchains]).to(device).contiguous() for q in Qs]
+        logpts_dev = torch.empty((nchains, n_out), dtype=torch.float64, device=device)
+        like_dev = torch.empty((nchains,), dtype=torch.float64, device=device)
+        like_all = torch.empty((n_gpus * nchains,), dtype=torch.float64, device=device) if n_gpus > 1 else None
+        logpts_pin = torch.empty((nchains, n_out), dtype=torch.float64).pin_memory()
+        like_pin = torch.empty((nchains,), dtype=torch.float64).pin_memory()
+        qp = [q_pin[r][:nchains] for r in range(n_rot)]             # leading rows of a pinned C-contiguous matrix: contiguous
+
+        def step_resident(i):
+            ev.eval_device(q_dev[i % n_rot], logpts_dev, like_dev)
+            if n_gpus > 1 and gather_every_step:
+                dist.all_gather_into_tensor(like_all, like_dev)
+
+        def step_e2e(i):
+            ev.eval_pinned(nchains, qp[i % n_rot].data_ptr(), logpts_pin.data_ptr(), like_pin.data_ptr())
+            if n_gpus > 1 and gather_every_step:
+                like_dev.copy_(like_pin, non_blocking=True)
+                dist.all_gather_into_tensor(like_all, like_dev)
+
+        step_resident(0)                            # binds the ctx to torch's current stream: torch events bracket our kernels
+        torch.cuda.synchronize(device)
+        viol = ev.ctx.index_violations()
+        if viol:
+            raise SystemExit("bench.py: %d library index violations in the synthetic chains" % viol)
+        if not torch.isfinite(like_dev).all():
+            raise SystemExit("bench.py: non-finite llk in the synthetic chains")
+        sampler = ClockSampler(local_rank) if (rank == 0 and with_clocks) else None   # polling before the warm-up
+        for i in range(warmup):
+            step_resident(i)
+        barrier()
+        ev.ctx.stack_ms_accum(reset=True)
+        launches0 = ev.ctx.launch_count()
+        t_wall0 = time.perf_counter()
+        e0.record()
+        for i in range(steps):
+            step_resident(i)
+        e1.record()
+        barrier()
+        t_wall1 = time.perf_counter()
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
+        launches = ev.ctx.launch_count() - launches0
+        k_sum, k_n = ev.ctx.stack_ms_accum(reset=True)             # the K event pairs recorded inside the timed loop
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        out = {"ms_per_step": ms_total / steps, "value": n_gpus * nchains * steps / (ms_total / 1e3),
+               "kernel_ms": k_sum / max(1, k_n), "kernel_evals": int(k_n),
+               "kernel_share_of_step": max_over_ranks(k_sum) / ms_total, "launches": int(launches), "clocks": clocks}
+        if n_gpus > 1 and not gather_every_step:
+            # the stage-boundary exchange, on its own: llk of every chain to every rank (beat_b200.distributed)
+            barrier()
+            e0.record()
             dist.all_gather_into_tensor(like_all, like_dev)
+            e1.record()
+            barrier()
+            out["allgather_llk_ms"] = max_over_ranks(e0.elapsed_time(e1))
+        if with_e2e:
+            for i in range(max(1, warmup // 2)):
+                step_e2e(i)
+            barrier()
+            e0.record()
+            for i in range(steps):
+                step_e2e(i)
+            e1.record()
+            barrier()
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+            assert np.isfinite(like_pin.numpy()).all()
+            out["e2e_value"] = n_gpus * nchains * steps / (ms_e2e / 1e3)
+            out["e2e_ms_per_step"] = ms_e2e / steps
+        out["q_dev"], out["bufs"] = q_dev, (logpts_dev, like_dev)
+        return out
 
-    # bind the ctx to torch's current stream so torch events bracket our kernels
-    ev.eval_device(q_dev[0], logpts_dev, like_dev)
-    torch.cuda.synchronize(device)
-    viol = ev.ctx.index_violations()
-    if viol:
-        raise SystemExit("bench.py: %d library index violations in the synthetic chains" % viol)
-    if not torch.isfinite(like_dev).all():
-        raise SystemExit("bench.py: non-finite llk in the synthetic chains")
+    # ---------------- headline: f32 library, `chains` per GPU (weak scaling), all-gather of llk every step for N > 1
+    ev = make_evaluator(args.store)
+    head = measure(ev, args.store, B, args.steps, args.warmup, gather_every_step=True, with_clocks=True)
+    log("value %.0f evals/s (%.2f ms/step, stack+misfit %.2f ms)" % (head["value"], head["ms_per_step"], head["kernel_ms"]))
+    blocking = ev.ctx.stack_blocking(ev.wmap_ids[0], len(prob["slip_vars"]))
 
-    log("first evaluation ok (stack kernel %.2f ms); timing" % ev.ctx.last_stack_ms())
-    # ---------------- value: inputs resident in HBM
-    sampler = ClockSampler(local_rank) if rank == 0 else None       # polling before the warm-up: samples exist from step 0
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
-    launches0 = ev.ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stack_ms = []
-    t_wall0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        step_resident(i)
-    e1.record()
-    barrier()
-    t_wall1 = time.perf_counter()
-    ms_total = e0.elapsed_time(e1)
-    launches = ev.ctx.launch_count() - launches0
-    # duration of the dominant kernel (event pair recorded inside the library around the stack + misfit launches,
-    # on the same stream): read for a few more steps OUTSIDE the timed region so the event sync costs nothing there
-    for i in range(min(5, args.steps)):
-        step_resident(i)
-        stack_ms.append(ev.ctx.last_stack_ms())
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-    if n_gpus > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    value = n_gpus * B * args.steps / (ms_total / 1e3)
-
-    log("value %.0f evals/s (%.2f ms/step)" % (value, ms_total / args.steps))
-    # ---------------- e2e: host buffers through the C-ABI host entry
-    for i in range(max(1, args.warmup // 2)):
-        step_e2e(i)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step_e2e(i)
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if n_gpus > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_gpus * B * args.steps / (float(t.item()) / 1e3)
-    host_like = like_pin.numpy().copy()
-    assert np.isfinite(host_like).all()
+    # ---------------- strong scaling: the configuration as BASELINE.json names it -- n_chains = 4000 partitioned over the N
+    # ranks (reference: sampler/smc.py:423-427, base.py:534-535); the llk all-gather happens once per stage, as in SMC
+    strong = None
+    if n_gpus > 1 and not args.quick and B % n_gpus == 0:
+        per = B // n_gpus
+        sm = measure(ev, args.store, per, args.steps, args.warmup, gather_every_step=False)
+        t0 = ev.starttimes(per)                                          # rupture onset times of the last evaluated batch
+        touched = touched_library_bytes(prob, a, args.store, args.interpolation, Qs[(args.steps - 1) % n_rot][:per], t0) if rank == 0 else 0
+        peak = load_peaks()["hbm_gbs"]
+        strong = {"global_chains": B, "chains_per_gpu": per, "value": sm["value"], "unit": UNIT, "ms_per_step": sm["ms_per_step"],
+                  "e2e": sm.get("e2e_value"), "kernel_ms": sm["kernel_ms"], "kernel_share_of_step": sm["kernel_share_of_step"],
+                  "allgather_llk_ms_per_stage": sm.get("allgather_llk_ms"),
+                  "collective": "none inside the timed steps; one all-gather of llk[%d] per stage, timed separately" % B,
+                  "touched_library_bytes_per_gpu": touched,
+                  "hbm": {"achieved_GBps": touched / (sm["kernel_ms"] / 1e3) / 1e9 if touched else None, "peak_GBps": peak,
+                          "frac": (touched / (sm["kernel_ms"] / 1e3) / 1e9 / peak) if touched else None,
+                          "what": "distinct library rows the rank's chains gather in a step (each row crosses HBM once when "
+                                  "the gather is L2-perfect) / stack+misfit kernel time"}}
+        log("strong: %d chains/GPU -> %.0f evals/s (%.3f ms/step)" % (per, sm["value"], sm["ms_per_step"]))
 
     # ---------------- the same evaluation inside the lock-step Metropolis driver (propose -> bounds -> eval -> accept),
-    # everything resident on the device: what a sampler stage actually achieves per GPU
+    # everything resident on the device: what a sampler stage actually achieves per GPU; then with the trace writer on
     from beat_b200.sampler import BatchedMetropolis
     lower = np.concatenate([prob["priors"][n][0] for n, _ in prob["var_order"]])
     upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
     mh = BatchedMetropolis(ev.eval_device, lower, upper, B, device=device, tune=True, tune_interval=5, seed=rank)
     mh.chol = torch.diag(torch.as_tensor((upper - lower) * 0.005, device=device))
     mh.beta = 0.1
-    qs = q_dev[0].clone()
+    qs = head["q_dev"][0].clone()
     lps, lks = mh.initial_llk(qs)
     for _ in range(args.warmup):
         qs, lps, lks, _ = mh.step(qs, lps, lks)
@@ -515,16 +583,21 @@ def _run_gpu_arm(args):
         qs, lps, lks, _ = mh.step(qs, lps, lks)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-    if n_gpus > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sampler_value = n_gpus * B * args.steps / (float(t.item()) / 1e3)
+    sampler_value = n_gpus * B * args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+    sampler_traced = None
+    if not args.no_trace_writer:
+        try:
+            sampler_traced = sampler_with_trace_writer(args, prob, mh, qs, lps, lks, B, n_gpus, rank, barrier, max_over_ranks)
+        except Exception as e:                                           # a full disk must not take the benchmark down
+            log("trace-writer leg failed: %r" % (e,))
+            sampler_traced = {"value": None, "error": repr(e)}
 
+    line = None
     if rank == 0:
         _pk = load_peaks()
         peak, peak_src = _pk["hbm_gbs"], _pk["source"]
         bytes_launch = algorithmic_bytes_per_eval(a, args.store, args.interpolation) * B
-        k_ms = float(np.mean(stack_ms))
+        k_ms = head["kernel_ms"]
         try:
             row_bytes = min(16384, max(16, (a["ns"] * (4 if args.store == "f32" else 8)) // 16 * 16))
             gather_peak = max(ev.ctx.probe_gather(0, 30 << 20, row_bytes, 2048, 3) for _ in range(2))
@@ -532,53 +605,140 @@ def _run_gpu_arm(args):
             log("gather probe failed: %s" % e)
             gather_peak = None
         achieved = bytes_launch / (k_ms / 1e3) / 1e9
+        # DRAM traffic of the stack kernel: from the committed ncu capture ONLY if it was taken with this very build
         traffic, tnote, l2_bytes = None, None, None
+        build_hash = beatlib.source_hash()
         tpath = os.path.join(ROOT, "profiles", "stack_kernel_traffic.json")
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
                 if (CONFIG == "c3" and NOISE == "exponential" and not args.quick and tj.get("chains") == B and tj.get("store") == args.store
-                        and tj.get("interpolation") == args.interpolation):
+                        and tj.get("interpolation") == args.interpolation and tj.get("source_hash") == build_hash):
                     traffic, tnote, l2_bytes = tj.get("dram_bytes_per_launch"), tj.get("note"), tj.get("l2_to_sm_bytes")
+                else:
+                    tnote = "profiles/stack_kernel_traffic.json was captured on another build / configuration (source hash %s, this build %s): traffic withheld" % (tj.get("source_hash"), build_hash)
             except Exception:
                 pass
         n_sm, dev_name = ev.ctx.device_info()
+        clocks = head["clocks"]
         line = {
-            "metric": metric_name(), "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus, B),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * prob["n_params"] * 8,
-                    "d2h_bytes_per_step": B * (n_out + 1) * 8},
-            "gpu_launches": int(launches),
+            "metric": metric_name(), "value": head["value"], "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE_LABEL[args.store], "data": "synthetic", "config": workload_config(args, n_gpus, B),
+            "e2e": {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": B * prob["n_params"] * 8,
+                    "d2h_bytes_per_step": B * (ev.n_out + 1) * 8, "ms_per_step": head["e2e_ms_per_step"],
+                    "vs_resident": head["e2e_value"] / head["value"]},
+            "gpu_launches": head["launches"],
             "sampler_step": {"value": sampler_value, "unit": "chain-steps/s",
-                             "what": "lock-step Metropolis step (proposal + bounds + batched eval + accept) with the population resident on the device"},
+                             "what": "lock-step Metropolis step (proposal + bounds + batched eval + accept) with the population resident on the device",
+                             "with_trace_writer": sampler_traced},
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "gf_stack_chunk_kernel+misfit_kernel (GF gather/stack + misfit)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": k_ms,
-                         "kernel_share_of_step": k_ms / (ms_total / args.steps),
+                         "kernel_ms_source": "mean of the %d CUDA-event pairs recorded around the kernels inside the timed loop" % head["kernel_evals"],
+                         "kernel_share_of_step": head["kernel_share_of_step"],
+                         "build_source_hash": build_hash,
+                         "l2_blocking": blocking,
                          # frac > 1 is expected here, not a measurement error: the gather is L2-blocked, DRAM moves
                          # `traffic` bytes (ncu) for `algorithmic_bytes_per_launch` requested; the binding resource
                          # is the L2->SM fabric, reported below against 64 B/clk/SM
                          "l2_fabric": {"bytes_per_launch": l2_bytes,
                                        "achieved_GBps": (l2_bytes / (k_ms / 1e3) / 1e9) if l2_bytes else None,
-                                       "peak_GBps": n_sm * 64 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9 if clocks else None,
+                                       "peak_GBps": n_sm * 64 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6 / 1e9,
                                        "peak_source": "n_sm x 64 B/clk x measured SM clock",
-                                       # measured live: pseudo-random 480-byte rows out of a 30 MB (L2-resident) working
+                                       # measured live: pseudo-random rows out of a 30 MB (L2-resident) working
                                        # set with the kernel's own access pattern (csrc/probe.cuh)
                                        "measured_gather_peak_GBps": gather_peak,
                                        "frac_of_measured_gather_peak": (achieved / gather_peak) if gather_peak else None},
                          "note": tnote},
         }
+        if strong is not None:
+            line["strong"] = strong
         if cpu_info is not None:
             line["cpu_baseline"] = cpu_info
-    else:
-        line = None
+    del head
     ev.close()
+    del ev
+    torch.cuda.empty_cache()
+
+    # ---------------- strict mode: the library stored in f64, every operation in f64 (the reference's precision end to end)
+    if not args.no_strict_f64 and args.store == "f32" and not args.quick:
+        try:
+            ev64 = make_evaluator("f64")
+            s64 = measure(ev64, "f64", B, args.steps, args.warmup, gather_every_step=True)
+            if rank == 0:
+                b64 = algorithmic_bytes_per_eval(a, "f64", args.interpolation) * B
+                peak = load_peaks()["hbm_gbs"]
+                ach = b64 / (s64["kernel_ms"] / 1e3) / 1e9
+                line["strict_f64"] = {"dtype": DTYPE_LABEL["f64"], "value": s64["value"], "unit": UNIT, "ms_per_step": s64["ms_per_step"],
+                                      "e2e": s64["e2e_value"], "gf_library_GB_per_gpu": lib_bytes(a, "f64") / 1e9,
+                                      "l2_blocking": ev64.ctx.stack_blocking(ev64.wmap_ids[0], len(prob["slip_vars"])),
+                                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                                   "traffic": None, "algorithmic_bytes_per_launch": b64, "kernel_ms": s64["kernel_ms"],
+                                                   "kernel_share_of_step": s64["kernel_share_of_step"]}}
+                log("strict f64: %.0f evals/s (%.2f ms/step)" % (s64["value"], s64["ms_per_step"]))
+            del s64
+            ev64.close()
+        except Exception as e:
+            log("strict f64 leg failed: %r" % (e,))
+            if rank == 0:
+                line["strict_f64"] = {"value": None, "error": repr(e)}
     if n_gpus > 1:
         dist.destroy_process_group()
     return line
+
+
+def sampler_with_trace_writer(args, prob, mh, qs, lps, lks, B, n_gpus, rank, barrier, max_over_ranks):
+    """The lock-step Metropolis step with every chain's record of every step written in the reference's binary trace
+    format (beat/backend.py:651-897; beat_b200.backend.BatchedNumpyChains): D2H of the step's outputs into a pinned
+    buffer, structured-array packing, one append per chain and flush.  A few steps only: 4000 chain files per rank."""
+    import shutil
+    import tempfile
+    from collections import OrderedDict
+    import torch
+    from beat_b200.backend import BatchedNumpyChains
+    shapes = OrderedDict()
+    for name, n in prob["var_order"]:
+        shapes[name] = (int(n),)
+    shapes["seis_like"] = (int(lps.shape[1]),)
+    shapes["like"] = ()
+    steps = max(2, min(args.steps, 5))
+    d = tempfile.mkdtemp(prefix="beat_b200_trace_r%d_" % rank)
+    try:
+        w = BatchedNumpyChains(d, shapes, B, buffer_size=steps)
+        w.setup()
+        host_q = torch.empty(qs.shape, dtype=torch.float64).pin_memory()
+        host_lp = torch.empty(lps.shape, dtype=torch.float64).pin_memory()
+        host_lk = torch.empty(lks.shape, dtype=torch.float64).pin_memory()
+        off = prob["offsets"]
+
+        def record(q, lp, lk):
+            host_q.copy_(q, non_blocking=True); host_lp.copy_(lp, non_blocking=True); host_lk.copy_(lk, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            qn = host_q.numpy()
+            vals = {name: qn[:, off[name]:off[name] + n] for name, n in prob["var_order"]}
+            vals["seis_like"], vals["like"] = host_lp.numpy(), host_lk.numpy()
+            w.write(vals)
+
+        qs, lps, lks, _ = mh.step(qs, lps, lks)
+        record(qs, lps, lks)
+        w.flush()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            qs, lps, lks, _ = mh.step(qs, lps, lks)
+            record(qs, lps, lks)
+        w.flush()
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        nbytes = steps * B * w.data_structure.itemsize
+        return {"value": n_gpus * B * steps / dt, "unit": "chain-steps/s", "steps": steps,
+                "bytes_written_per_rank": int(nbytes), "write_MBps_per_rank": nbytes / dt / 1e6,
+                "what": "same step + D2H of q/logpts/like + one NumpyChain-format record per chain per step appended to %d chain files per rank (wall clock)" % B}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def run_c2_llk(args):
@@ -752,6 +912,8 @@ def main():
     ap.add_argument("--interpolation", default="multilinear", choices=["multilinear", "nearest_neighbor"])
     ap.add_argument("--quick", action="store_true", help="tiny shapes (development only; not a valid benchmark)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-strict-f64", action="store_true", help="skip the strict (f64 library) leg of the C3 line")
+    ap.add_argument("--no-trace-writer", action="store_true", help="skip the sampler step with the trace writer on")
     ap.add_argument("--noise", default="exponential", choices=["exponential", "variance", "dense"],
                     help="data covariance structure (exponential = BASELINE config; dense = full non-Toeplitz, for the record)")
     ap.add_argument("--ragged", action="store_true", help="config c2: GF records of uneven span (exercises the end-value path)")

@@ -328,9 +328,12 @@ int beatgpu_geom_timeouts(beatgpu_ctx* ctx, int64_t* count);
 /* Diagnostics (not on the product path): measured ceiling of the access pattern the GF stacking uses.  Gathers
  * pseudo-random rows of row_bytes (multiple of 16, <= 16384) from a zero-filled working set of ws_bytes with
  * mode 0 = one warp-wide 16-byte-per-lane load per row (gf_stack_chunk_kernel's pattern), mode 1 = one bulk
- * asynchronous copy (TMA) per row into shared memory which the warp then reads, mode 2 = the bulk copies alone.
- * A working set well below the 126 MB L2 measures the L2->SM path, one far above it the HBM gather rate.
- * bench.py reports the stack kernel against this number.                                                    */
+ * asynchronous copy (TMA) per row and per mbarrier into shared memory which the warp then reads, mode 2 = those bulk
+ * copies alone, mode 3 / 4 = the same with BATCHED copies (16 rows per mbarrier, 16 lanes issuing, 3 batches in flight
+ * per warp; 3 reads the rows back, 4 only ingests), mode 5 = rows already resident in shared memory (what a row-staged
+ * kernel would read), mode 6 / 7 / 8 = rows gathered from the shared memory of a cluster of 2 / 4 / 8 CTAs (DSMEM).
+ * A working set well below the 126 MB L2 measures the L2->SM path, one far above it the HBM gather rate (modes 5..8
+ * ignore it).  bench.py reports the stack kernel against the mode-0 number.                                 */
 int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_bytes, int rows_per_warp,
                          int n_launch, float* ms_per_launch, double* bytes_per_launch);
 
