@@ -98,6 +98,8 @@ def c3_args(quick):
         return dict(nt=8, subfaults=((5, 8, 2.0),), ns=40, ndur=5, nst=40)
     if CONFIG == "c4":      # joint geodetic + seismic FFI, dense non-Toeplitz geodetic covariance, laplacian prior
         return dict(nt=64, subfaults=((10, 20, 2.0),), ns=120, ndur=17, nst=64, geodetic=dict(nobs=[500]), laplacian=True)
+    if CONFIG == "c3big":   # C3 with a 4x larger per-patch library block (128 start times x 240 samples): exercises the L2-derived chunk
+        return dict(nt=16, subfaults=((10, 20, 2.0),), ns=240, ndur=17, nst=128)
     if CONFIG == "c5":      # multi-fault FFI, 2 segments x 150 patches
         return dict(nt=64, subfaults=((10, 15, 2.0), (10, 15, 2.0)), ns=120, ndur=17, nst=64)
     return dict(nt=64, subfaults=((10, 20, 2.0),), ns=120, ndur=17, nst=64)
@@ -107,7 +109,8 @@ def workload_config(args, n_gpus, chains):
     a = c3_args(args.quick)
     nd, nstr, h = a["subfaults"][0]
     npatch = sum(x[0] * x[1] for x in a["subfaults"])
-    extra = {"c3": "", "c4": " + geodetic static (500 obs, dense non-Toeplitz C) + laplacian prior",
+    extra = {"c3": "", "c3big": " (per-patch library block 4x that of C3)",
+             "c4": " + geodetic static (500 obs, dense non-Toeplitz C) + laplacian prior",
              "c5": " (2 subfaults x %d patches)" % (nd * nstr)}[CONFIG if not args.quick else "c3"]
     return {
         "workload": "%s FFI seismic: %d patches (%dx%d, %.1f km) x %d targets x %d samples, library %d durations x %d "
@@ -548,7 +551,7 @@ def _run_gpu_arm(args):
     # ---------------- strong scaling: the configuration as BASELINE.json names it -- n_chains = 4000 partitioned over the N
     # ranks (reference: sampler/smc.py:423-427, base.py:534-535); the llk all-gather happens once per stage, as in SMC
     strong = None
-    if n_gpus > 1 and not args.quick and B % n_gpus == 0:
+    if n_gpus > 1 and not args.quick and B % n_gpus == 0 and CONFIG == "c3":
         per = B // n_gpus
         sm = measure(ev, args.store, per, args.steps, args.warmup, gather_every_step=False)
         t0 = ev.starttimes(per)                                          # rupture onset times of the last evaluated batch
@@ -664,7 +667,7 @@ def _run_gpu_arm(args):
     torch.cuda.empty_cache()
 
     # ---------------- strict mode: the library stored in f64, every operation in f64 (the reference's precision end to end)
-    if not args.no_strict_f64 and args.store == "f32" and not args.quick:
+    if not args.no_strict_f64 and args.store == "f32" and not args.quick and CONFIG == "c3":
         try:
             ev64 = make_evaluator("f64")
             s64 = measure(ev64, "f64", B, args.steps, args.warmup, gather_every_step=True)
@@ -917,7 +920,7 @@ def main():
     ap.add_argument("--noise", default="exponential", choices=["exponential", "variance", "dense"],
                     help="data covariance structure (exponential = BASELINE config; dense = full non-Toeplitz, for the record)")
     ap.add_argument("--ragged", action="store_true", help="config c2: GF records of uneven span (exercises the end-value path)")
-    ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5", "c2llk", "c2"], help="c3 = BASELINE.json metric; c4/c5 for the record")
+    ap.add_argument("--config", default="c3", choices=["c3", "c3big", "c4", "c5", "c2llk", "c2"], help="c3 = BASELINE.json metric; c4/c5 for the record")
     args = ap.parse_args()
     global CONFIG, NOISE
     CONFIG, NOISE = args.config, args.noise
