@@ -45,3 +45,71 @@ def test_batched_chains_byte_compatible(tmp_path):
         np.testing.assert_array_equal(got, np.array([st["seis_like"][c] for st in steps]))
         np.testing.assert_array_equal(bk.get_values(w.filename(c), "like", burn=n_steps - 1)[0], steps[-1]["like"][c])
     assert bk.create_flat_names("x", (2, 2)) == ["x__0_0", "x__0_1", "x__1_0", "x__1_1"] and bk.create_flat_names("like", ()) == ["like"]
+
+
+def _golden_trace():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trace_golden.npz"))
+
+
+def test_files_byte_identical_to_the_references_numpychain(tmp_path):
+    """Fixture written by the REFERENCE'S OWN NumpyChain (beat/backend.py:651-897: setup -> write x 7 with a buffer of 3
+    -> record_buffer; tests/golden/make_trace_golden.py): the batched writer produces the same bytes, file by file, and
+    at generation time the reference's reader read our files back identically."""
+    g = _golden_trace()
+    assert bool(g["reference_reader_reads_our_files"])
+    names = [str(n) for n in g["varnames"]]
+    var_shapes = OrderedDict((n, tuple(int(x) for x in str(s).strip("()").split(",") if x.strip())) for n, s in zip(names, g["shapes"]))
+    n_chains, n_steps = int(g["n_chains"]), int(g["n_steps"])
+    for buffer_size in (int(g["buffer_size"]), 1, 100):                  # flush granularity must not matter
+        w = bk.BatchedNumpyChains(str(tmp_path / ("b%d" % buffer_size)), var_shapes, n_chains, buffer_size=buffer_size)
+        w.setup()
+        for i in range(n_steps):
+            w.write({n: g["step%d_%s" % (i, n)] for n in names})
+        w.flush()
+        for c in range(n_chains):
+            ours = open(w.filename(c), "rb").read()
+            assert ours == g["file_chain%d" % c].tobytes(), (buffer_size, c)
+            assert ours.startswith(g["header"].tobytes())
+    # and the reader half: the reference-written bytes parse into the values that were written
+    for c in range(n_chains):
+        path = str(tmp_path / ("ref-chain-%d.bin" % c))
+        open(path, "wb").write(g["file_chain%d" % c].tobytes())
+        for n in names:
+            want = np.array([g["step%d_%s" % (i, n)][c] for i in range(n_steps)]).reshape((n_steps,) + var_shapes[n])
+            np.testing.assert_array_equal(bk.get_values(path, n), want)
+
+
+def test_smc_driver_streams_every_step_into_chain_files(tmp_path):
+    """The lock-step SMC driver with the trace writer on its ``on_step`` hook: after the run every chain file of every
+    stage holds n_steps records whose last one is that chain's end point (what the reference's stage directories hold,
+    beat/backend.py:985-1156 / sampler/base.py:364,390)."""
+    import torch
+    from beat_b200 import sampler as S
+    n, n_chains, n_steps = 3, 24, 6
+    mu = torch.tensor([0.3, -0.2, 0.1], dtype=torch.float64)
+
+    def evaluator(q):
+        lp = -0.5 * ((q - mu) ** 2 / 0.05).sum(dim=1, keepdim=True)
+        return lp, lp[:, 0]
+
+    var_shapes = OrderedDict([("x", (n,)), ("seis_like", (1,)), ("like", ())])
+    writers = {}
+
+    def on_step(stage, step, q, logpts, like):
+        if stage not in writers:
+            w = bk.BatchedNumpyChains(str(tmp_path / ("stage_%d" % stage)), var_shapes, n_chains, buffer_size=4)
+            w.setup()
+            writers[stage] = w
+        writers[stage].write({"x": q.cpu().numpy(), "seis_like": logpts.cpu().numpy(), "like": like.cpu().numpy()})
+
+    res = S.smc_sample(evaluator, -np.ones(n), np.ones(n), n_chains, n_steps, seed=3, on_step=on_step)
+    for w in writers.values():
+        w.flush()
+    assert len(writers) == res["n_stages"] and res["n_stages"] >= 2
+    last = writers[max(writers)]
+    for c in range(n_chains):
+        x = bk.get_values(last.filename(c), "x")
+        assert x.shape == (n_steps, n)
+        np.testing.assert_array_equal(x[-1], res["population"][c])
+        np.testing.assert_array_equal(bk.get_values(last.filename(c), "like")[-1], res["likelihoods"][c])

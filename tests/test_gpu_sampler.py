@@ -50,3 +50,52 @@ def test_smc_ffi_small_posterior_concentrates():
     assert (out["population"] >= lower).all() and (out["population"] <= upper).all()
     assert out["n_evals"] > n_chains
     ev.close()
+
+
+def test_smc_ffi_with_trace_writer_on_the_gpu(tmp_path):
+    """The sampler run a user would do: lock-step SMC on the batched CUDA evaluator with every step of every chain
+    streamed into the reference's binary trace format (row f4 driven by row f1).  The files hold n_steps records per
+    stage; the last record of each chain is its end point, and re-evaluating a stored point reproduces its stored logpts."""
+    import torch
+    from collections import OrderedDict
+    from beat_b200 import backend as bk
+    from beat_b200 import sampler as S
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=5, subfaults=((3, 4, 4.0),), ns=40, ndur=4, seed=15)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    dev = torch.device("cuda", 0)
+    lower = np.concatenate([prob["priors"][n][0] for n, _ in prob["var_order"]])
+    upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
+    n_chains, n_steps = 64, 5
+    shapes = OrderedDict((name, (int(n),)) for name, n in prob["var_order"])
+    shapes["seis_like"] = (ev.n_out,)
+    shapes["like"] = ()
+    off = prob["offsets"]
+    writers = {}
+
+    def on_step(stage, step, q, logpts, like):
+        if stage not in writers:
+            writers[stage] = bk.BatchedNumpyChains(str(tmp_path / ("stage_%d" % stage)), shapes, n_chains, buffer_size=3)
+            writers[stage].setup()
+        qn = q.cpu().numpy()
+        vals = {name: qn[:, off[name]:off[name] + n] for name, n in prob["var_order"]}
+        vals["seis_like"], vals["like"] = logpts.cpu().numpy(), like.cpu().numpy()
+        writers[stage].write(vals)
+
+    out = S.smc_sample(ev.eval_device, lower, upper, n_chains=n_chains, n_steps=n_steps, device=dev, seed=2, max_stages=4, on_step=on_step)
+    for w in writers.values():
+        w.flush()
+    assert len(writers) == out["n_stages"]
+    last = writers[max(writers)]
+    for c in (0, 17, 63):
+        rec, _ = bk.read_chain(last.filename(c))
+        assert rec.shape[0] == n_steps
+        q_last = np.concatenate([rec[name][-1].ravel() for name, _ in prob["var_order"]])
+        np.testing.assert_array_equal(q_last, out["population"][c])
+        np.testing.assert_array_equal(rec["like"][-1], out["likelihoods"][c])
+        lp, lk = ev(q_last[None, :])
+        np.testing.assert_allclose(rec["seis_like"][-1].ravel(), lp[0], rtol=1e-12)
+        ref = O.ffi_seismic_eval(prob, synthetic.split_point(prob, q_last), impl="port")
+        np.testing.assert_allclose(rec["seis_like"][-1].ravel(), ref, rtol=1e-9)
+    assert ev.drain_diagnostics()["index_violations"] == 0
+    ev.close()
