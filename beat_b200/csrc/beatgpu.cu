@@ -139,6 +139,7 @@ struct beatgpu_ctx {
     bool persistent = false;        // BEATGPU_PERSISTENT=1: fused kernel with one resident CTA wave walking the items
     int stack_mode = 1;             // 0 = fused kernel (CTA per target x chain), 1 = patch-chunked warps + misfit pass
     int chunk_patches = 32;         // BEATGPU_CHUNK: target patches per chunk (<= 32)
+    int chunk_occ = 5;              // BEATGPU_CHUNK_OCC: 5 / 6 / 7 CTAs per SM guaranteed by the chunk kernel's register allocation
     int geo_mode = 1;               // 1 = FP64 tensor-core GEMM tiles (BEATGPU_GEO_MODE=mma), 0 = one CTA per (chain, dataset)
     double* d_partial = nullptr;    // [B, nt, nchunk, ns] scratch of the chunked path
     size_t partial_bytes = 0;
@@ -333,12 +334,19 @@ int launch_chunk_nvar(beatgpu_ctx* ctx, const ChunkArgs& ca)
     const long n_items = (long)ca.s.nt * ca.nchunk * ca.s.B;
     const long grid = (n_items + kChunkWarps - 1) / kChunkWarps;
     if (grid > 2147483647L) return fail(ctx, BEATGPU_E_ARG, "grid too large: %ld", grid);
+#define LAUNCH_CHUNK(NV)                                                                                            \
+    do {                                                                                                            \
+        if (ctx->chunk_occ >= 7) gf_stack_chunk_kernel<T, K, NV, 7><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca);      \
+        else if (ctx->chunk_occ == 6) gf_stack_chunk_kernel<T, K, NV, 6><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); \
+        else gf_stack_chunk_kernel<T, K, NV, 5><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca);                          \
+    } while (0)
     switch (ca.s.nvar) {
-        case 1: gf_stack_chunk_kernel<T, K, 1><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); break;
-        case 2: gf_stack_chunk_kernel<T, K, 2><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); break;
-        case 3: gf_stack_chunk_kernel<T, K, 3><<<(unsigned)grid, kChunkWarps * 32, 0, ctx->stream>>>(ca); break;
+        case 1: LAUNCH_CHUNK(1); break;
+        case 2: LAUNCH_CHUNK(2); break;
+        case 3: LAUNCH_CHUNK(3); break;
         default: return fail(ctx, BEATGPU_E_ARG, "n_slipvars must be 1..3, got %d", ca.s.nvar);
     }
+#undef LAUNCH_CHUNK
     CKL();
     return BEATGPU_OK;
 }
@@ -402,6 +410,7 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
 {
     ChunkArgs ca;
     ca.s = a;
+    ca.zero_mask = 0u;
     derive_chunk(ctx, w, a.nvar, a.np, &ca.chunk, &ca.nchunk, nullptr);
     const size_t need = (size_t)a.B * a.nt * ca.nchunk * a.ns * sizeof(double);
     if (ctx->partial_bytes < need) {
@@ -515,6 +524,13 @@ int set_lib_meta(beatgpu_ctx* ctx, WaveMap& w, int store_dtype, const int64_t di
         for (int i = 0; i < 5; ++i) same = same && (w.dims[i] == dims[i]);
         if (!same) return fail(ctx, BEATGPU_E_ARG, "all slip components of a wavemap must share dims, axes and storage dtype");
     }
+    {   // the kernels address a row as a 32-bit offset in 16-byte units (PatchPlan::off): < 64 GB per slip component
+        const long ld = row_stride_for(w.ns, store_dtype);
+        const long long units = (long long)dims[0] * dims[1] * dims[2] * dims[3] * (ld * (store_dtype == BEATGPU_F32 ? 4 : 8) / 16);
+        if (units > 0xFFFFFFFFLL)
+            return fail(ctx, BEATGPU_E_ARG, "library of %.1f GB per slip component exceeds the 64 GB the row offsets can address",
+                        (double)units * 16.0 / 1e9);
+    }
     w.store_dtype = store_dtype;
     for (int i = 0; i < 5; ++i) w.dims[i] = dims[i];
     w.ld = row_stride_for(w.ns, store_dtype);
@@ -562,6 +578,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_FILTER_CAP")) { int v = atoi(e); if (v == 80 || v == 0) c->filter_cap = v; }
     if (const char* e = getenv("BEATGPU_GEOM_HALF")) { int v = atoi(e); if (v >= 2 && v <= 4) c->geom_half = v; }
     if (const char* e = getenv("BEATGPU_CHUNK")) { int v = atoi(e); if (v >= 1 && v <= kChunkMax) { c->chunk_patches = v; c->chunk_forced = true; } }
+    if (const char* e = getenv("BEATGPU_CHUNK_OCC")) { int v = atoi(e); if (v >= 5 && v <= 7) c->chunk_occ = v; }
     if (const char* e = getenv("BEATGPU_L2_FRAC")) { double v = atof(e); if (v > 0.0 && v <= 4.0) c->l2_frac = v; }
     if (const char* e = getenv("BEATGPU_SPLIT_H2D")) c->split_h2d = atoi(e) != 0;
     *out = c;
@@ -1599,7 +1616,8 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
         a.rows_per_warp = std::max(kBatchRows, rows_per_warp / kBatchRows * kBatchRows);
     } else if (smem_only) {
         cluster = 1 << (mode - 5);
-        rows_smem = std::max(1, (32 * 1024) / row_bytes);
+        rows_smem = 1;
+        while (rows_smem * 2 * row_bytes <= 32 * 1024) rows_smem *= 2;      // power of two (the kernel masks)
         smem = (size_t)rows_smem * row_bytes;
         per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, (size_t)(216 * 1024) / (smem + 1024)));
         CK(cudaFuncSetAttribute(probe_dsmem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

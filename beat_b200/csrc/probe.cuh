@@ -58,6 +58,22 @@ __global__ void __launch_bounds__(kProbeThreads) probe_ldg_kernel(ProbeArgs a)
 #pragma unroll
             for (int u = 0; u < kProbeDepth; ++u) acc += v[u].x + v[u].y + v[u].z + v[u].w;
         }
+    } else if (a.row_bytes <= 1024) {
+        // f64-library rows (960 B): two 16-byte loads per lane per row, kProbeDepth rows in flight (the f64 stack kernel's pattern)
+        const bool act0 = lane * 16 < a.row_bytes, act1 = (lane + 32) * 16 < a.row_bytes;
+        for (int it = 0; it < a.rows_per_warp; it += kProbeDepth) {
+            float4 v0[kProbeDepth], v1[kProbeDepth];
+#pragma unroll
+            for (int u = 0; u < kProbeDepth; ++u) {
+                const long r = probe_hash(gw * 7919u + (uint32_t)(it + u)) & a.row_mask;
+                const float4* row = (const float4*)(a.ws + r * a.row_stride);
+                v0[u] = v1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act0) v0[u] = __ldg(row + lane);
+                if (act1) v1[u] = __ldg(row + lane + 32);
+            }
+#pragma unroll
+            for (int u = 0; u < kProbeDepth; ++u) acc += v0[u].x + v0[u].y + v0[u].z + v0[u].w + v1[u].x + v1[u].y + v1[u].z + v1[u].w;
+        }
     } else {
         const int nvec = a.row_bytes / 16;
         for (int it = 0; it < a.rows_per_warp; ++it) {
@@ -221,10 +237,12 @@ __global__ void __launch_bounds__(kProbeThreads) probe_dsmem_kernel(ProbeArgs a,
         float4 v[kProbeDepth];
 #pragma unroll
         for (int u = 0; u < kProbeDepth; ++u) {
-            const uint32_t h = probe_hash(gw * 7919u + (uint32_t)(it + u));
-            const uint32_t r = (h >> 8) % (uint32_t)rows_smem;
+            // cheap row pick (the probe must not be issue-bound): one multiply-add, masks instead of modulos
+            // (rows_smem and cluster_size are powers of two)
+            const uint32_t h = (gw * 7919u + (uint32_t)(it + u)) * 2654435761u;
+            const uint32_t r = (h >> 12) & (uint32_t)(rows_smem - 1);
             uint32_t addr = base + r * (uint32_t)a.row_bytes + (uint32_t)lane * 16u;
-            if (cluster_size > 1) addr = mapa_shared(addr, (h & 0xffu) % (uint32_t)cluster_size);
+            if (cluster_size > 1) addr = mapa_shared(addr, (h >> 4) & (uint32_t)(cluster_size - 1));
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (active) v[u] = ld_shared_cluster_v4(addr);
         }

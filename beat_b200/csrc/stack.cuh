@@ -67,7 +67,9 @@ struct StackArgs {
 // WT = float for f32 libraries (weights are rounded once, like the library values themselves), double for f64.
 template <typename WT, int K, int NVAR>
 struct __align__(16) PatchPlan {
-    int row[4];                // library row index of each tap (already moved onto a valid row when its weight is zero)
+    uint32_t off[4];           // offset of each tap's library row in 16-BYTE UNITS (row index * row_bytes / 16; rows are 16-byte
+                               // multiples and a library is < 64 GB, checked at upload): one IMAD.WIDE per row turns it into
+                               // the load address.  Taps with zero weight already point at a valid row.
     WT w[K * NVAR];            // weight of tap k, slip variable v at w[v*K + k]
 };
 
@@ -76,6 +78,68 @@ template <typename T> __device__ __forceinline__ int slot_sample(int j, int e);
 template <> __device__ __forceinline__ int slot_sample<float>(int j, int e) { return 4 * j + e; }
 // f64 rows are read as two 16-byte vectors per lane: vector j covers samples 2j,2j+1 and vector j+32 covers 64+2j,64+2j+1
 template <> __device__ __forceinline__ int slot_sample<double>(int j, int e) { return (e < 2) ? (2 * j + e) : (64 + 2 * j + (e - 2)); }
+
+// Plan of one (chain, target, patch): library row offsets + f64-computed weights, exactly the reference's index
+// arithmetic (beat/ffi/base.py:506-517 start times, :553-564 durations, :676-679 multilinear weights; station
+// correction beat/models/seismic.py:1283-1291).  Returns true when a tap with non-zero weight leaves the library.
+template <typename T, int K, int NVAR>
+__device__ __forceinline__ bool make_patch_plan(const StackArgs& a, int c, int t, int p, double dur_p, double st_p, double corr,
+                                                PatchPlan<T, K, NVAR>& pl)
+{
+    const double x = (dur_p - a.dur_min) / a.dur_step;                        // base.py:556 / :561
+    const double y = ((st_p - corr) - a.st_min) / a.st_step;                  // seismic.py:1283-1291, base.py:509 / :514
+    const long rows_per_patch = (long)a.ndur * a.nst;
+    const long base = ((long)t * a.np + p) * rows_per_patch;
+    const uint32_t row16 = (uint32_t)(a.ld * (long)sizeof(T) / 16);           // 16-byte units per row
+    bool viol;
+    if (K == 1) {                                                             // nearest neighbour (base.py:506-512,553-559)
+        const int di = (int)rint(x);          // round-half-even; the int16 cast of the reference cannot matter in range
+        const int si = (int)rint(y);
+        viol = (x != x) || (y != y) || (di < 0) || (di >= a.ndur) || (si < 0) || (si >= a.nst);
+        pl.off[0] = viol ? 0u : (uint32_t)(base + (long)di * a.nst + si) * row16;
+        pl.off[1] = pl.off[2] = pl.off[3] = 0u;
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v) pl.w[v] = (T)a.slip[v][(long)c * a.slip_sc[v] + p];
+    } else {                                                                  // multilinear (base.py:513-517,560-564,662-679)
+        const int dc = (int)ceil(x);
+        const int sc = (int)ceil(y);
+        const double rf = (double)dc - x;
+        const double sf = (double)sc - y;
+        // a "floor" tap has weight exactly 0 when the coordinate is integral; numpy then reads a wrapped (valid) row and
+        // multiplies by 0 -- we read the ceil row instead.  Any tap with non-zero weight outside the library is a violation.
+        const int dfl = (rf == 0.0) ? dc : dc - 1;
+        const int sfl = (sf == 0.0) ? sc : sc - 1;
+        viol = (x != x) || (y != y) || (dc < 0) || (dc >= a.ndur) || (dfl < 0) || (sc < 0) || (sc >= a.nst) || (sfl < 0);
+        if (viol) {
+            pl.off[0] = pl.off[1] = pl.off[2] = pl.off[3] = 0u;
+        } else {
+            pl.off[0] = (uint32_t)(base + (long)dc * a.nst + sc) * row16;      // st ceil,  rt ceil
+            pl.off[1] = (uint32_t)(base + (long)dc * a.nst + sfl) * row16;     // st floor, rt ceil
+            pl.off[2] = (uint32_t)(base + (long)dfl * a.nst + sc) * row16;     // st ceil,  rt floor
+            pl.off[3] = (uint32_t)(base + (long)dfl * a.nst + sfl) * row16;    // st floor, rt floor
+        }
+        const double w_cc = (1.0 - sf) * (1.0 - rf);
+        const double w_fc = sf * (1.0 - rf);
+        const double w_cf = (1.0 - sf) * rf;
+        const double w_ff = sf * rf;
+#pragma unroll
+        for (int v = 0; v < NVAR; ++v) {
+            const double u = a.slip[v][(long)c * a.slip_sc[v] + p];
+            pl.w[v * K + 0] = (T)(w_cc * u);
+            pl.w[v * K + 1] = (T)(w_fc * u);
+            pl.w[v * K + 2] = (T)(w_cf * u);
+            pl.w[v * K + 3] = (T)(w_ff * u);
+        }
+    }
+    if (viol) {
+#pragma unroll
+        for (int q = 0; q < K * NVAR; ++q) pl.w[q] = (T)0;
+    }
+    return viol;
+}
+
+// address of 16-byte vector `vec` of the row at plan offset `off16` (one IMAD.WIDE.U32 + the load)
+__device__ __forceinline__ const char* row_ptr(const char* lane_base, uint32_t off16) { return lane_base + (size_t)off16 * 16u; }
 
 template <typename T, int K, int NVAR, bool WRITE_SYNTH>
 __global__ void __launch_bounds__(kStackThreads)
@@ -107,7 +171,6 @@ gf_stack_misfit_kernel(StackArgs a)
     const double* st = a.st + (long)c * a.st_sc + (long)t * a.st_st;
     double corr = 0.0;
     if (a.corr) corr = a.corr[(long)c * a.corr_sc + a.station_idx[t]];
-    const long rows_per_patch = (long)a.ndur * a.nst;
 
     for (int s0 = 0; s0 < a.ns; s0 += kWindow) {
         const int wlen = min(kWindow, a.ns - s0);
@@ -120,55 +183,10 @@ gf_stack_misfit_kernel(StackArgs a)
             // ---------------- (1) plan: indices + weights, f64, reference arithmetic ----------------
             for (int i = tid; i < pn; i += kStackThreads) {
                 const int p = p0 + i;
-                const double x = (dur[p] - a.dur_min) / a.dur_step;                       // base.py:556 / :561
-                const double y = ((st[p] - corr) - a.st_min) / a.st_step;                 // seismic.py:1283-1291, base.py:509 / :514
-                const long base = ((long)t * a.np + p) * rows_per_patch;
                 Plan pl;
-                bool viol = false;
-                if (K == 1) {                                                            // nearest neighbour (base.py:506-512,553-559)
-                    const int di = (int)rint(x);          // round-half-even; the int16 cast of the reference cannot matter in range
-                    const int si = (int)rint(y);
-                    viol = (x != x) || (y != y) || (di < 0) || (di >= a.ndur) || (si < 0) || (si >= a.nst);
-                    pl.row[0] = viol ? 0 : (int)(base + (long)di * a.nst + si);
-#pragma unroll
-                    for (int v = 0; v < NVAR; ++v) pl.w[v] = (T)a.slip[v][(long)c * a.slip_sc[v] + p];
-                } else {                                                                 // multilinear (base.py:513-517,560-564,662-679)
-                    const int dc = (int)ceil(x);
-                    const int sc = (int)ceil(y);
-                    const double rf = (double)dc - x;
-                    const double sf = (double)sc - y;
-                    // a "floor" tap has weight exactly 0 when the coordinate is integral; numpy then reads a wrapped
-                    // (valid) row and multiplies by 0 -- we read the ceil row instead.  Any tap with non-zero weight
-                    // outside the library is a violation.
-                    const int dfl = (rf == 0.0) ? dc : dc - 1;
-                    const int sfl = (sf == 0.0) ? sc : sc - 1;
-                    viol = (x != x) || (y != y) || (dc < 0) || (dc >= a.ndur) || (dfl < 0) || (sc < 0) || (sc >= a.nst) || (sfl < 0);
-                    if (viol) {
-                        pl.row[0] = pl.row[1] = pl.row[2] = pl.row[3] = 0;
-                    } else {
-                        pl.row[0] = (int)(base + (long)dc * a.nst + sc);      // st ceil,  rt ceil
-                        pl.row[1] = (int)(base + (long)dc * a.nst + sfl);     // st floor, rt ceil
-                        pl.row[2] = (int)(base + (long)dfl * a.nst + sc);     // st ceil,  rt floor
-                        pl.row[3] = (int)(base + (long)dfl * a.nst + sfl);    // st floor, rt floor
-                    }
-                    const double w_cc = (1.0 - sf) * (1.0 - rf);
-                    const double w_fc = sf * (1.0 - rf);
-                    const double w_cf = (1.0 - sf) * rf;
-                    const double w_ff = sf * rf;
-#pragma unroll
-                    for (int v = 0; v < NVAR; ++v) {
-                        const double u = a.slip[v][(long)c * a.slip_sc[v] + p];
-                        pl.w[v * K + 0] = (T)(w_cc * u);
-                        pl.w[v * K + 1] = (T)(w_fc * u);
-                        pl.w[v * K + 2] = (T)(w_cf * u);
-                        pl.w[v * K + 3] = (T)(w_ff * u);
-                    }
-                }
-                if (viol) {
+                if (make_patch_plan<T, K, NVAR>(a, c, t, p, dur[p], st[p], corr, pl)) {
                     if (s0 == 0) atomicAdd(a.violations, 1ULL);
                     s_bad = 1;
-#pragma unroll
-                    for (int q = 0; q < K * NVAR; ++q) pl.w[q] = (T)0;
                 }
                 plan[i] = pl;
             }
@@ -189,7 +207,7 @@ gf_stack_misfit_kernel(StackArgs a)
                         for (int v = 0; v < NVAR; ++v)
 #pragma unroll
                             for (int k = 0; k < K; ++k) {
-                                const float* row = reinterpret_cast<const float*>(a.G[v]) + (long)plan[ii].row[k] * a.ld + s0;
+                                const char* row = row_ptr(reinterpret_cast<const char*>(a.G[v]) + (size_t)s0 * sizeof(float), plan[ii].off[k]);
                                 g[u][v * K + k] = ld_on ? __ldg(reinterpret_cast<const float4*>(row) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
                             }
                     }
@@ -223,7 +241,7 @@ gf_stack_misfit_kernel(StackArgs a)
                     for (int v = 0; v < NVAR; ++v)
 #pragma unroll
                         for (int k = 0; k < K; ++k) {
-                            const double* row = reinterpret_cast<const double*>(a.G[v]) + (long)plan[i].row[k] * a.ld + s0;
+                            const char* row = row_ptr(reinterpret_cast<const char*>(a.G[v]) + (size_t)s0 * sizeof(double), plan[i].off[k]);
                             g0[v * K + k] = act0 ? __ldg(reinterpret_cast<const double2*>(row) + lane) : make_double2(0.0, 0.0);
                             g1[v * K + k] = act1 ? __ldg(reinterpret_cast<const double2*>(row) + lane + 32) : make_double2(0.0, 0.0);
                         }
@@ -391,11 +409,15 @@ struct ChunkArgs {
     StackArgs s;                          // library, axes and per-chain inputs as for the fused kernel
     int chunk;                            // patches per chunk (<= kChunkMax)
     int nchunk;
+    uint32_t zero_mask;                   // always 0; opaque to the compiler (load-scheduling dependence, see the kernel)
     double* partial;                      // [B, nt, nchunk, ns]
 };
 
-template <typename T, int K, int NVAR>
-__global__ void __launch_bounds__(kChunkWarps * 32)
+// MINB: CTAs per SM the register allocation must allow (__launch_bounds__): 5 leaves the multilinear kernels their natural
+// ~96 registers (16 row loads of two patches in flight per lane), 6 / 7 cap them at 80 / 72 (more resident warps, fewer
+// loads in flight each); selected at run time (BEATGPU_CHUNK_OCC), default from measurements (profiles/README.md).
+template <typename T, int K, int NVAR, int MINB>
+__global__ void __launch_bounds__(kChunkWarps * 32, MINB)
 gf_stack_chunk_kernel(ChunkArgs ca)
 {
     using Plan = PatchPlan<T, K, NVAR>;
@@ -417,58 +439,13 @@ gf_stack_chunk_kernel(ChunkArgs ca)
     const double* st = a.st + (long)c * a.st_sc + (long)t * a.st_st;
     double corr = 0.0;
     if (a.corr) corr = a.corr[(long)c * a.corr_sc + a.station_idx[t]];
-    const long rows_per_patch = (long)a.ndur * a.nst;
-
     // ---- plan (one lane per patch; same arithmetic as the fused kernel / ffi/base.py:506-517,553-564,676-679)
     bool viol = false;
     if (lane < pn) {
         const int p = p0 + lane;
-        const double x = (dur[p] - a.dur_min) / a.dur_step;
-        const double y = ((st[p] - corr) - a.st_min) / a.st_step;
-        const long base = ((long)t * a.np + p) * rows_per_patch;
         Plan pl;
-        if (K == 1) {
-            const int di = (int)rint(x);
-            const int si = (int)rint(y);
-            viol = (x != x) || (y != y) || (di < 0) || (di >= a.ndur) || (si < 0) || (si >= a.nst);
-            pl.row[0] = viol ? 0 : (int)(base + (long)di * a.nst + si);
-            pl.row[1] = pl.row[2] = pl.row[3] = 0;
-#pragma unroll
-            for (int v = 0; v < NVAR; ++v) pl.w[v] = (T)a.slip[v][(long)c * a.slip_sc[v] + p];
-        } else {
-            const int dc = (int)ceil(x);
-            const int sc = (int)ceil(y);
-            const double rf = (double)dc - x;
-            const double sf = (double)sc - y;
-            const int dfl = (rf == 0.0) ? dc : dc - 1;
-            const int sfl = (sf == 0.0) ? sc : sc - 1;
-            viol = (x != x) || (y != y) || (dc < 0) || (dc >= a.ndur) || (dfl < 0) || (sc < 0) || (sc >= a.nst) || (sfl < 0);
-            if (viol) {
-                pl.row[0] = pl.row[1] = pl.row[2] = pl.row[3] = 0;
-            } else {
-                pl.row[0] = (int)(base + (long)dc * a.nst + sc);
-                pl.row[1] = (int)(base + (long)dc * a.nst + sfl);
-                pl.row[2] = (int)(base + (long)dfl * a.nst + sc);
-                pl.row[3] = (int)(base + (long)dfl * a.nst + sfl);
-            }
-            const double w_cc = (1.0 - sf) * (1.0 - rf);
-            const double w_fc = sf * (1.0 - rf);
-            const double w_cf = (1.0 - sf) * rf;
-            const double w_ff = sf * rf;
-#pragma unroll
-            for (int v = 0; v < NVAR; ++v) {
-                const double u = a.slip[v][(long)c * a.slip_sc[v] + p];
-                pl.w[v * K + 0] = (T)(w_cc * u);
-                pl.w[v * K + 1] = (T)(w_fc * u);
-                pl.w[v * K + 2] = (T)(w_cf * u);
-                pl.w[v * K + 3] = (T)(w_ff * u);
-            }
-        }
-        if (viol) {
-            atomicAdd(a.violations, 1ULL);
-#pragma unroll
-            for (int q = 0; q < K * NVAR; ++q) pl.w[q] = (T)0;
-        }
+        viol = make_patch_plan<T, K, NVAR>(a, c, t, p, dur[p], st[p], corr, pl);
+        if (viol) atomicAdd(a.violations, 1ULL);
         plan[lane] = pl;
     }
     const bool any_viol = __any_sync(0xffffffffu, viol);
@@ -479,30 +456,43 @@ gf_stack_chunk_kernel(ChunkArgs ca)
         const int wlen = min(kWindow, a.ns - s0);
         const int nvec = (wlen * (int)sizeof(T) + 15) / 16;
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        // Every lane loads unconditionally: lanes past the end of the row re-read its last vector (valid memory, the
+        // value is never stored), so the row loop carries no predicates and no zero fills; the address of a row is one
+        // IMAD.WIDE (plan offset in 16-byte units) on a per-lane base pointer.
         if (sizeof(T) == 4) {
             // rows of PF patches in flight per lane.  Measured at C3, nearest neighbour: PF = 2 / 4 / 8 -> 789 k / 840 k /
             // 732 k evals/s (depth vs registers/occupancy); multilinear already has 8*NVAR loads per patch.
             constexpr int PF = (K == 1) ? 4 : 2;
-            const bool active = lane < nvec;
-            for (int i = 0; i < pn; i += PF) {
+            const char* gb[NVAR];
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v)
+                gb[v] = reinterpret_cast<const char*>(a.G[v]) + (size_t)s0 * sizeof(float) + (size_t)min(lane, nvec - 1) * 16u;
+            int i = 0;
+            for (; i + PF <= pn; i += PF) {
                 float4 g[PF][K * NVAR];
 #pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    const bool has = (i + u) < pn;
-                    const int ii = has ? i + u : i;
-                    const bool ld_on = active && has;
+                for (int u = 0; u < PF; ++u)
 #pragma unroll
                     for (int v = 0; v < NVAR; ++v)
 #pragma unroll
-                        for (int k = 0; k < K; ++k) {
-                            const float* row = reinterpret_cast<const float*>(a.G[v]) + (long)plan[ii].row[k] * a.ld + s0;
-                            g[u][v * K + k] = ld_on ? __ldg(reinterpret_cast<const float4*>(row) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                }
-                float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int k = 0; k < K; ++k)
+                            g[u][v * K + k] = __ldg(reinterpret_cast<const float4*>(row_ptr(gb[v], plan[i + u].off[k])));
+                // Every row load of the group must be in flight before the first product is formed: left alone, ptxas pairs
+                // each load with its use to save registers and the in-order issue then stalls on the first product with
+                // two loads outstanding instead of sixteen.  The partial sums therefore START from a zero that is data
+                // dependent on all loads (OR of one word of each, masked with a kernel argument that is 0): exact (+0.0f),
+                // a handful of LOP3s, and no product can issue before the last load has.
+                uint32_t dep = 0u;
 #pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    if ((i + u) >= pn) break;
+                for (int u = 0; u < PF; ++u)
+#pragma unroll
+                    for (int q = 0; q < K * NVAR; ++q) dep |= __float_as_uint(g[u][q].x);
+                const float zero = __uint_as_float(dep & ca.zero_mask);
+                // f32 library: products and the PF*K*NVAR-term partial sum in f32 (FFMA pipe), one f32->f64 conversion per
+                // element per patch group; the running sum over patches stays f64.
+                float4 part = make_float4(zero, zero, zero, zero);
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
 #pragma unroll
                     for (int q = 0; q < K * NVAR; ++q) {
                         const float w = plan[i + u].w[q];
@@ -511,6 +501,28 @@ gf_stack_chunk_kernel(ChunkArgs ca)
                         part.z = fmaf(w, g[u][q].z, part.z);
                         part.w = fmaf(w, g[u][q].w, part.w);
                     }
+                acc[0] += (double)part.x;
+                acc[1] += (double)part.y;
+                acc[2] += (double)part.z;
+                acc[3] += (double)part.w;
+            }
+            if (i < pn) {                                        // remainder (< PF patches): one group, same arithmetic
+                float4 part = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (; i < pn; ++i) {
+                    float4 g[K * NVAR];
+#pragma unroll
+                    for (int v = 0; v < NVAR; ++v)
+#pragma unroll
+                        for (int k = 0; k < K; ++k)
+                            g[v * K + k] = __ldg(reinterpret_cast<const float4*>(row_ptr(gb[v], plan[i].off[k])));
+#pragma unroll
+                    for (int q = 0; q < K * NVAR; ++q) {
+                        const float w = plan[i].w[q];
+                        part.x = fmaf(w, g[q].x, part.x);
+                        part.y = fmaf(w, g[q].y, part.y);
+                        part.z = fmaf(w, g[q].z, part.z);
+                        part.w = fmaf(w, g[q].w, part.w);
+                    }
                 }
                 acc[0] += (double)part.x;
                 acc[1] += (double)part.y;
@@ -518,20 +530,34 @@ gf_stack_chunk_kernel(ChunkArgs ca)
                 acc[3] += (double)part.w;
             }
         } else {
-            const bool act0 = lane < nvec, act1 = (lane + 32) < nvec;
+            // f64 storage: a window of 128 samples = 64 16-byte vectors; lane reads vectors `lane` and `lane+32`
+            const char* gb0[NVAR];
+            const char* gb1[NVAR];
+#pragma unroll
+            for (int v = 0; v < NVAR; ++v) {
+                const char* b = reinterpret_cast<const char*>(a.G[v]) + (size_t)s0 * sizeof(double);
+                gb0[v] = b + (size_t)min(lane, nvec - 1) * 16u;
+                gb1[v] = b + (size_t)min(lane + 32, nvec - 1) * 16u;
+            }
             for (int i = 0; i < pn; ++i) {
                 double2 g0[K * NVAR], g1[K * NVAR];
 #pragma unroll
                 for (int v = 0; v < NVAR; ++v)
 #pragma unroll
                     for (int k = 0; k < K; ++k) {
-                        const double* row = reinterpret_cast<const double*>(a.G[v]) + (long)plan[i].row[k] * a.ld + s0;
-                        g0[v * K + k] = act0 ? __ldg(reinterpret_cast<const double2*>(row) + lane) : make_double2(0.0, 0.0);
-                        g1[v * K + k] = act1 ? __ldg(reinterpret_cast<const double2*>(row) + lane + 32) : make_double2(0.0, 0.0);
+                        g0[v * K + k] = __ldg(reinterpret_cast<const double2*>(row_ptr(gb0[v], plan[i].off[k])));
+                        g1[v * K + k] = __ldg(reinterpret_cast<const double2*>(row_ptr(gb1[v], plan[i].off[k])));
                     }
+                // all 2*K*NVAR loads in flight before the first FMA (see the f32 branch): the first weight carries a data
+                // dependence on every load (its high word OR 0), and each accumulator chain starts with that weight
+                uint32_t dep = 0u;
+#pragma unroll
+                for (int q = 0; q < K * NVAR; ++q) dep |= (uint32_t)__double2hiint(g0[q].x) | (uint32_t)__double2hiint(g1[q].x);
+                dep &= ca.zero_mask;
 #pragma unroll
                 for (int q = 0; q < K * NVAR; ++q) {
-                    const double w = plan[i].w[q];
+                    double w = plan[i].w[q];
+                    if (q == 0) w = __hiloint2double(__double2hiint(w) | (int)dep, __double2loint(w));
                     acc[0] = fma(w, g0[q].x, acc[0]);
                     acc[1] = fma(w, g0[q].y, acc[1]);
                     acc[2] = fma(w, g1[q].x, acc[2]);

@@ -289,7 +289,7 @@ class SeisSynthesizer(_OpBase):
         output[0][0] = synths if batched else synths[0]
         output[1][0] = tmins.copy() if batched else tmins[0].copy()
 
-    def make_node(self, inputs):  # pragma: no cover - needs pytensor
+    def make_node(self, inputs):
         """``inputs``: dict of named tensors, exactly like the reference (pytensorf.py:215-239)."""
         self.varnames = list(inputs.keys())
         inlist = [_tt.as_tensor_variable(i) for i in inputs.values()]

@@ -64,9 +64,14 @@ class Sweeper(_OpBase):
             self._ctx = ctx
         return self._ctx
 
-    def make_node(self, *inputs):  # pragma: no cover - needs pytensor
+    def make_node(self, *inputs):
+        """As the reference (pytensorf.py:432-441): inputs wrapped with ``as_tensor_variable``, output type taken from a
+        zero array of ``infer_shape``; a slowness MATRIX [B, np] (the batch axis this Op adds) declares a matrix output."""
         inlist = [_tt.as_tensor_variable(i) for i in inputs]
-        outv = _tt.as_tensor_variable(np.zeros(self.infer_shape()[0]))
+        shape = self.infer_shape()[0]
+        if getattr(inlist[0], "ndim", 1) == 2:
+            shape = (1,) + tuple(shape)
+        outv = _tt.as_tensor_variable(np.zeros(shape))
         return _Apply(self, inlist, [outv.type()])
 
     def perform(self, node, inputs, output):
@@ -86,7 +91,10 @@ class Sweeper(_OpBase):
         output[0][0] = out[0] if single else out
 
     def infer_shape(self, fgraph=None, node=None, input_shapes=None):
-        return [(self.n_patch_dip * self.n_patch_strike,)]
+        n = self.n_patch_dip * self.n_patch_strike                          # pytensorf.py:502-503
+        if input_shapes and len(input_shapes[0]) == 2:
+            return [(input_shapes[0][0], n)]
+        return [(n,)]
 
 
 def _times2idxs(x, x_min, x_step, interpolation):
@@ -254,8 +262,10 @@ class FFILogLike(_OpBase):
         self.evaluator = evaluator
         self.name = name
 
-    def make_node(self, q):  # pragma: no cover - needs pytensor
+    def make_node(self, q):
         q = _tt.as_tensor_variable(q)
+        if getattr(q, "ndim", 1) == 2:                                       # [B, n_params]: logpts [B, n_out], like [B]
+            return _Apply(self, [q], [_tt.dmatrix(), _tt.dvector()])
         return _Apply(self, [q], [_tt.dvector(), _tt.dscalar()])
 
     def perform(self, node, inputs, output):
@@ -268,4 +278,6 @@ class FFILogLike(_OpBase):
             output[0][0], output[1][0] = logpts, like
 
     def infer_shape(self, fgraph=None, node=None, input_shapes=None):
+        if input_shapes and len(input_shapes[0]) == 2:
+            return [(input_shapes[0][0], self.evaluator.n_out), (input_shapes[0][0],)]
         return [(self.evaluator.n_out,), ()]

@@ -347,21 +347,40 @@ def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_in
     ``alpha = (beta2 - beta1) * (llk1 - llk2)`` (pt.py:428-455), counting acceptances per pair and re-scaling the
     temperature ladder every ``beta_tune_interval`` samples.  Here all chains advance together (one batched evaluation
     per step); after each interval the chains are paired at random and every pair proposes a swap with the same rule.
-    Returns the recorded samples of the beta = 1 chains."""
+
+    Sharded over ranks (torch.distributed, one process per GPU): every rank advances ``n_chains / world`` chains.  A
+    swap exchanges the two chains' TEMPERATURE LEVELS (beta and the Metropolis scaling tuned at that level) instead of
+    their states -- the same Markov chain on (state, level) pairs, but no particle ever moves between GPUs.  The swap
+    phase is one all-gather of (llk, scaling, acceptance counter) per chain -- 3 x 8 bytes x n_chains -- and the
+    decisions are taken identically on every rank from a shared host RNG.
+
+    Returns the recorded samples of the chains that were at beta = 1 when recorded (all ranks' records, rank order)."""
     import torch
+    from . import distributed as D
     device = device if device is not None else torch.device("cpu")
-    rng = np.random.default_rng(seed)
+    rng = np.random.default_rng(seed)                                        # shared by all ranks: identical decisions
     lower = np.asarray(lower, dtype=np.float64)
     upper = np.asarray(upper, dtype=np.float64)
     n_params = lower.size
-    mh = BatchedMetropolis(evaluator, lower, upper, n_chains, device=device, tune=True, tune_interval=tune_interval, seed=seed * 7919 + 1)
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    lo, hi = D.shard_range(n_chains, rank, world)
+    n_local = hi - lo
+    mh = BatchedMetropolis(evaluator, lower, upper, n_local, device=device, tune=True, tune_interval=tune_interval,
+                           seed=seed * 7919 + 1 + rank)
     if proposal_cov is None:
         proposal_cov = np.diag(((upper - lower) * 0.05) ** 2)
     mh.set_proposal_covariance(proposal_cov)
-    betas = pt_betas(n_chains, n_chains_posterior, t_scale)
-    mh.beta = torch.as_tensor(betas, device=device)
+    ladder = pt_betas(n_chains, n_chains_posterior, t_scale)                 # beta of every temperature level
+    level = np.arange(n_chains)                                              # level held by each chain (replicated)
+
+    def set_local_betas():
+        mh.beta = torch.as_tensor(ladder[level[lo:hi]], device=device)
+
+    set_local_betas()
     pop = rng.uniform(lower, upper, (n_chains, n_params)) if initial_population is None else np.array(initial_population, dtype=np.float64)
-    q = torch.as_tensor(pop, device=device).contiguous()
+    q = torch.as_tensor(pop[lo:hi], device=device).contiguous()
     logpts, like = mh.initial_llk(q)
 
     recorded, rec_like = [], []
@@ -372,38 +391,54 @@ def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_in
     while done < n_samples:
         draws = int(rng.integers(swap_interval[0], swap_interval[1]))        # pt.py:146-149 (DiscreteBoundedUniform)
         draws = min(draws, n_samples - done)
+        post_local = torch.as_tensor(np.flatnonzero(level[lo:hi] < n_chains_posterior), device=device)
         for i in range(draws):
             q, logpts, like, _ = mh.step(q, logpts, like)
-            if (done + i) % record_every == 0:
-                recorded.append(q[:n_chains_posterior].clone())
-                rec_like.append(like[:n_chains_posterior].clone())
+            if (done + i) % record_every == 0 and post_local.numel():
+                recorded.append(q[post_local].clone())
+                rec_like.append(like[post_local].clone())
         done += draws
-        # swap proposals between randomly paired chains (pt.py:428-455)
+        # ---- swap proposals between randomly paired chains (pt.py:428-455); THE exchange of this sampler
+        packed = torch.stack([like, mh.scaling, mh.accepted], dim=1)         # [n_local, 3]
+        allp = D.allgather_chains(packed).cpu().numpy()                      # [n_chains, 3] on every rank
+        like_all, scal_all, accd_all = allp[:, 0].copy(), allp[:, 1].copy(), allp[:, 2].copy()
         perm = rng.permutation(n_chains)
-        a = torch.as_tensor(perm[0: 2 * (n_chains // 2): 2].copy(), device=device)
-        b = torch.as_tensor(perm[1: 2 * (n_chains // 2): 2].copy(), device=device)
-        beta_t = mh.beta
-        alpha = (beta_t[b] - beta_t[a]) * (like[a] - like[b])
-        u = torch.as_tensor(rng.random(a.numel()), device=device)
-        acc = torch.log(u) < alpha
+        a, b = perm[0: 2 * (n_chains // 2): 2], perm[1: 2 * (n_chains // 2): 2]
+        beta_all = ladder[level]
+        alpha = (beta_all[b] - beta_all[a]) * (like_all[a] - like_all[b])
+        with np.errstate(invalid="ignore"):
+            acc = np.log(rng.random(a.size)) < alpha
         ia, ib = a[acc], b[acc]
-        if ia.numel():
-            q = q.clone()
-            logpts, like = logpts.clone(), like.clone()
-            qa, la, lpa = q[ia].clone(), like[ia].clone(), logpts[ia].clone()
-            q[ia], like[ia], logpts[ia] = q[ib], like[ib], logpts[ib]
-            q[ib], like[ib], logpts[ib] = qa, la, lpa
+        if ia.size:
+            # accepted: the two chains trade places on the ladder; the step size tuned for a level stays with the level
+            level[ia], level[ib] = level[ib].copy(), level[ia].copy()
+            scal_all[ia], scal_all[ib] = scal_all[ib].copy(), scal_all[ia].copy()
+            accd_all[ia], accd_all[ib] = accd_all[ib].copy(), accd_all[ia].copy()
+            mh.scaling = torch.as_tensor(scal_all[lo:hi], device=device).contiguous()
+            mh.accepted = torch.as_tensor(accd_all[lo:hi], device=device).contiguous()
+            set_local_betas()
         k = int(acc.sum())
-        n_swaps += a.numel(); n_acc += k
-        since_tune_swaps += a.numel(); since_tune_acc += k
+        n_swaps += a.size; n_acc += k
+        since_tune_swaps += a.size; since_tune_acc += k
         if beta_tune_interval and since_tune_swaps >= beta_tune_interval:
             rate = since_tune_acc / float(since_tune_swaps)
             t_scale = float(np.clip(float(tune_scale(torch.tensor([t_scale], dtype=torch.float64),
                                                       torch.tensor([rate], dtype=torch.float64))[0]), 1.01, 2.0))   # pt.py:126-127
-            mh.beta = torch.as_tensor(pt_betas(n_chains, n_chains_posterior, t_scale), device=device)
+            ladder = pt_betas(n_chains, n_chains_posterior, t_scale)
+            set_local_betas()
             scales.append(t_scale)
             since_tune_swaps = since_tune_acc = 0
-    samples = torch.stack(recorded).reshape(-1, n_params).cpu().numpy()
-    return dict(samples=samples, likelihoods=torch.stack(rec_like).reshape(-1).cpu().numpy(), betas=np.asarray(mh.beta.cpu()),
-                swap_acceptance=n_acc / max(1, n_swaps), t_scales=scales, n_evals=mh.n_evals,
-                population=q.cpu().numpy(), population_likelihoods=like.cpu().numpy())
+    if recorded:
+        samples_local = torch.cat(recorded).reshape(-1, n_params).cpu().numpy()
+        like_local = torch.cat(rec_like).reshape(-1).cpu().numpy()
+    else:
+        samples_local, like_local = np.zeros((0, n_params)), np.zeros(0)
+    parts = D.gather_objects((samples_local, like_local))                     # ragged per rank: once, at the end
+    samples = np.concatenate([p[0] for p in parts])
+    likes = np.concatenate([p[1] for p in parts])
+    n_evals = torch.tensor([mh.n_evals], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(n_evals)
+    return dict(samples=samples, likelihoods=likes, betas=ladder, chain_betas=ladder[level], levels=level.copy(),
+                swap_acceptance=n_acc / max(1, n_swaps), t_scales=scales, n_evals=int(n_evals.item()),
+                population=D.allgather_chains(q).cpu().numpy(), population_likelihoods=D.allgather_chains(like).cpu().numpy())

@@ -441,6 +441,13 @@ def _run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     a = c3_args(args.quick)
+    # c4 / c5 are named with a GLOBAL population (BASELINE.json: n_chains = 2000 on 4 GPUs; PT with 512 chains on 8 GPUs),
+    # partitioned over the ranks like the reference partitions n_chains over its workers (sampler/smc.py:423-427)
+    global_chains = args.global_chains or ({"c4": 2000, "c5": 512}.get(CONFIG) if args.chains == 4000 else None)
+    if global_chains:
+        if global_chains % n_gpus:
+            raise SystemExit("bench.py: n_chains / n_gpus has to be a whole number (%d / %d)" % (global_chains, n_gpus))
+        args.chains = global_chains // n_gpus
     B = args.chains
     prob = synthetic.make_problem(interpolation=args.interpolation, seed=1234, build_library=False, noise=args.noise, **a)
     n_rot = 3
@@ -595,6 +602,10 @@ def _run_gpu_arm(args):
             log("trace-writer leg failed: %r" % (e,))
             sampler_traced = {"value": None, "error": repr(e)}
 
+    pt_leg = None
+    if CONFIG == "c5" and not args.quick:
+        pt_leg = pt_driver_leg(args, ev, prob, lower, upper, B * n_gpus, n_gpus, rank, device, barrier, max_over_ranks)
+
     line = None
     if rank == 0:
         _pk = load_peaks()
@@ -659,6 +670,12 @@ def _run_gpu_arm(args):
         }
         if strong is not None:
             line["strong"] = strong
+        if pt_leg is not None:
+            line["pt_sampler"] = pt_leg
+        if global_chains:
+            line["scaling"] = "strong"
+            line["config"]["global_chains"] = global_chains
+            line["config"]["scaling_protocol"] = "strong: n_chains = %d partitioned over %d ranks" % (global_chains, n_gpus)
         if cpu_info is not None:
             line["cpu_baseline"] = cpu_info
     del head
@@ -691,6 +708,31 @@ def _run_gpu_arm(args):
     if n_gpus > 1:
         dist.destroy_process_group()
     return line
+
+
+def pt_driver_leg(args, ev, prob, lower, upper, n_chains, n_gpus, rank, device, barrier, max_over_ranks):
+    """BASELINE config 5 as named: the parallel-tempering driver with `n_chains` chains on a beta ladder, sharded over the
+    ranks (beat_b200.sampler.pt_sample; swap rule of the reference, beat/sampler/pt.py:442-446; its master / worker
+    processes :472-704 become one all-gather of (llk, scaling, acceptance) per swap interval)."""
+    import torch
+    from beat_b200 import sampler as S
+    from beat_b200 import synthetic
+    n_samples = max(60, 12 * args.steps)
+    pop = synthetic.draw_chains(prob, n_chains, seed=97)                  # identical on every rank
+    kw = dict(device=device, swap_interval=(10, 15), n_chains_posterior=max(1, n_chains // 8), t_scale=1.2,
+              beta_tune_interval=4 * n_chains, proposal_cov=np.diag(((upper - lower) * 0.005) ** 2), tune_interval=20,
+              initial_population=pop, record_every=10 ** 9)
+    S.pt_sample(ev.eval_device, lower, upper, n_chains, 30, seed=1, **kw)          # warm-up (scratch, NCCL, allocator)
+    barrier()
+    t0 = time.perf_counter()
+    out = S.pt_sample(ev.eval_device, lower, upper, n_chains, n_samples, seed=2, **kw)
+    barrier()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    return {"value": n_chains * n_samples / dt, "unit": "chain-steps/s", "n_chains": n_chains, "chains_per_gpu": n_chains // n_gpus,
+            "n_samples_per_chain": n_samples, "ms_per_step": 1e3 * dt / n_samples, "swap_acceptance": out["swap_acceptance"],
+            "n_evals": out["n_evals"], "t_scales": out["t_scales"][-3:],
+            "what": "lock-step PT: Metropolis step for every chain of the ladder + swap proposals every 10-15 steps "
+                    "(one all-gather of 3 doubles per chain); wall clock incl. the initial evaluation, max over ranks"}
 
 
 def sampler_with_trace_writer(args, prob, mh, qs, lps, lks, B, n_gpus, rank, barrier, max_over_ranks):
@@ -911,6 +953,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="beat_b200", choices=["beat_b200", "reference"])
     ap.add_argument("--chains", type=int, default=4000, help="chains per GPU")
+    ap.add_argument("--global-chains", type=int, default=0, help="population size partitioned over the ranks (c4: 2000, c5: 512 by default)")
     ap.add_argument("--store", default="f32", choices=["f32", "f64"], help="GF library storage dtype in HBM")
     ap.add_argument("--interpolation", default="multilinear", choices=["multilinear", "nearest_neighbor"])
     ap.add_argument("--quick", action="store_true", help="tiny shapes (development only; not a valid benchmark)")

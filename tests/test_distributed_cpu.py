@@ -138,3 +138,46 @@ def test_smc_checkpoint_resume_two_ranks(tmp_path):
         assert np.array_equal(z["fb"], z["rb"]) and z["fb"][-1] == 1.0
         assert np.array_equal(z["full"], z["res"])
         assert int(z["fe"]) == int(z["re"])
+
+
+def _pt_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from beat_b200 import distributed as D
+    from beat_b200 import sampler as S
+    D.init_process_group(backend="gloo")
+    n = 4
+    mu1 = torch.ones(n, dtype=torch.float64) * 0.5
+
+    def ev(q):          # the two-Gaussian toy posterior of the reference's test/test_pt.py
+        l1 = -0.5 * 100.0 * ((q - mu1) ** 2).sum(dim=1)
+        l2 = -0.5 * 100.0 * ((q + mu1) ** 2).sum(dim=1)
+        like = torch.logsumexp(torch.stack([np.log(0.1) + l1, np.log(0.9) + l2]), dim=0)
+        return like[:, None].clone(), like
+    out = S.pt_sample(ev, -2.0 * np.ones(n), 2.0 * np.ones(n), n_chains=16, n_samples=5000, swap_interval=(10, 15),
+                      n_chains_posterior=4, t_scale=1.6, beta_tune_interval=200, seed=5)
+    np.savez(os.path.join(out_dir, "pt_r%d.npz" % rank), samples=out["samples"], levels=out["levels"], betas=out["betas"],
+             chain_betas=out["chain_betas"], acc=out["swap_acceptance"], n_evals=out["n_evals"], pop=out["population"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_pt_sharded_over_two_ranks(tmp_path):
+    """Parallel tempering with the chains sharded over 2 ranks (gloo): the swap phase is one all-gather of (llk, scaling,
+    acceptance) per chain, decisions are identical on both ranks (shared host RNG), chains trade temperature LEVELS so no
+    state crosses ranks -- and the beta = 1 samples still recover the two-mode posterior of the reference's test
+    (swap rule: /root/reference/beat/sampler/pt.py:442-446)."""
+    port = _free_port()
+    mp.spawn(_pt_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(os.path.join(str(tmp_path), "pt_r0.npz"))
+    r1 = np.load(os.path.join(str(tmp_path), "pt_r1.npz"))
+    for k in ("samples", "levels", "betas", "chain_betas", "pop"):
+        assert np.array_equal(r0[k], r1[k]), k                      # both ranks hold the same global picture
+    assert sorted(r0["levels"].tolist()) == list(range(16))         # the ladder is a permutation of the chains
+    assert r0["betas"][0] == 1.0 and np.all(np.diff(r0["betas"][3:]) < 0)
+    assert 0.0 < float(r0["acc"]) <= 1.0 and int(r0["n_evals"]) > 16 * 1000
+    assert (r0["levels"] != np.arange(16)).any()                    # swaps did happen, across the rank boundary too
+    x = r0["samples"][len(r0["samples"]) // 5:]
+    assert x.shape[0] > 10000
+    np.testing.assert_allclose(np.abs(x).mean(axis=0), 0.5, rtol=0.0, atol=0.05)
+    assert 0.02 < (x[:, 0] > 0).mean() < 0.35

@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 
 def test_call_order_and_argument_errors():
-    from beat_b200.lib import BeatGpuError, Context, Layout, F64
+    from beat_b200.lib import BeatGpuError, Context, GFLibraryError, Layout, F64
     c = Context(0)
     with pytest.raises(BeatGpuError, match="set_fault"):
         c.fast_sweep_batch(0, np.ones((1, 4)), [0], [0])
@@ -30,8 +30,21 @@ def test_call_order_and_argument_errors():
     wid = c.add_wavemap(1, 8, "multilinear", None, [0], [8])
     with pytest.raises(BeatGpuError, match="not uploaded"):
         c.ffi_loglike_batch(np.ones((2, 4)))
-    with pytest.raises(ValueError, match="do not match"):
+    with pytest.raises(GFLibraryError, match="1 targets x 8 samples"):
         c.upload_gflib(wid, 0, np.zeros((2, 4, 2, 3, 8)), F64, 0.5, 0.5, 0.0, 0.5)     # wrong target count
+    with pytest.raises(ValueError, match="do not match"):                               # ... and the C side refuses it too
+        c.alloc_gflib(wid, 0, F64, (2, 4, 2, 3, 8), 0.5, 0.5, 0.0, 0.5)
+    # every operand is shape-checked before its pointer crosses the ABI (the C side reads nt*ns, nt*ns*ns, canon_len ... elements)
+    with pytest.raises(ValueError, match="expected shape"):
+        c.upload_data(wid, np.zeros((1, 7)))
+    with pytest.raises(ValueError, match="expected shape"):
+        c.update_weights(wid, np.zeros((1, 8, 7)), [0.0])
+    with pytest.raises(ValueError, match="expected shape"):
+        c.update_weights(wid, np.eye(8)[None], [0.0, 0.0])
+    with pytest.raises(ValueError, match="expected shape"):
+        c.set_layout(L, np.zeros(15))                                                   # fixed vector one short
+    with pytest.raises(ValueError, match="expected shape"):
+        c.set_laplacian(np.eye(5), 0.0, 0)
     with pytest.raises(ValueError, match="patches"):
         c.upload_gflib(wid, 0, np.zeros((1, 5, 2, 3, 8)), F64, 0.5, 0.5, 0.0, 0.5)     # wrong patch count
     c.upload_gflib(wid, 0, np.zeros((1, 4, 2, 3, 8)), F64, 0.5, 0.5, 0.0, 0.5)

@@ -16,9 +16,10 @@ def main():
     out = {"device": ctx.device_info()[1], "results": []}
     # 480 B = one GF-library row of the FFI stack kernel; 8448 B = one GF-store window of the delay-and-sum kernel
     quick = "--quick" in sys.argv
+    only = [int(x.split("=")[1]) for x in sys.argv if x.startswith("--mode=")]
     for row_bytes in ((480, 512, 960) if quick else (480, 512, 960, 2048, 8448)):
         for ws_mb in ((30,) if quick else (30, 512, 8192)):      # L2-resident (one stack-kernel chunk), > L2, >> L2
-            for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8):
+            for mode in (only or (0, 1, 2, 3, 4, 5, 6, 7, 8)):
                 if mode >= 5 and ws_mb != 30:
                     continue                                   # shared-memory modes have no working set
                 if mode in (3, 4) and row_bytes > 1024:
