@@ -96,9 +96,16 @@ def resample(weights, rng):
 
 
 class BatchedMetropolis:
-    """All chains of one rank advanced in lock-step.  ``evaluator(q_dev) -> (logpts, like)`` on torch tensors."""
+    """All chains of one rank advanced in lock-step.  ``evaluator(q_dev) -> (logpts, like)`` on torch tensors.
 
-    def __init__(self, evaluator, lower, upper, n_chains, device=None, scale=1.0, tune=True, tune_interval=100, seed=0):
+    ``cuda_graph=True`` (CUDA devices only): after two eager steps the whole step -- proposal draw, bounds check, the
+    batched evaluation (sweep -> stack -> misfit -> sum, launched by libbeatgpu on the capturing stream), accept / reject
+    and the in-place state update -- is captured into ONE CUDA graph and replayed.  With few chains per GPU (n_chains =
+    4000 over 8 GPUs = 500 per rank) the ~30 launches of a step otherwise cost more host time than the kernels take.
+    The population state then lives in fixed buffers that ``step`` updates in place and returns."""
+
+    def __init__(self, evaluator, lower, upper, n_chains, device=None, scale=1.0, tune=True, tune_interval=100, seed=0,
+                 cuda_graph=False):
         import torch
         self.torch = torch
         self.evaluator = evaluator
@@ -114,9 +121,22 @@ class BatchedMetropolis:
         self.accepted = torch.zeros(n_chains, dtype=torch.float64, device=self.device)
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(int(seed))
-        self.beta = 1.0
+        self._beta_t = torch.ones(n_chains, dtype=torch.float64, device=self.device)   # per-chain beta (SMC: all equal; PT: ladder)
         self._n_evals = torch.zeros((), dtype=torch.float64, device=self.device)   # device-side counter: no host sync per step
         self.chol = None
+        self.cuda_graph = bool(cuda_graph) and torch.device(self.device).type == "cuda"
+        self._graph, self._gstream, self._eager_steps, self._state = None, None, 0, None
+
+    @property
+    def beta(self):
+        return self._beta_t
+
+    @beta.setter
+    def beta(self, value):
+        """Scalar (SMC stage beta) or one value per chain (PT ladder); written in place (the captured graph reads it)."""
+        torch = self.torch
+        v = torch.as_tensor(value, dtype=torch.float64, device=self.device) if not torch.is_tensor(value) else value.to(self.device, torch.float64)
+        self._beta_t.copy_(v.expand(self.n_chains) if v.ndim == 0 else v)
 
     @property
     def n_evals(self):
@@ -132,7 +152,12 @@ class BatchedMetropolis:
 
     def set_proposal_covariance(self, cov):
         """MultivariateNormal proposal (sampler/base.py:163-167): draws = z @ chol(cov).T."""
-        self.chol = self.torch.as_tensor(proposal_factor(cov), device=self.device)
+        f = self.torch.as_tensor(proposal_factor(cov), device=self.device)
+        if self.chol is not None and self.chol.shape == f.shape:
+            self.chol.copy_(f)                       # in place: a captured graph keeps reading the same buffer
+        else:
+            self.chol = f.contiguous()
+            self._graph = None
 
     def initial_llk(self, q):
         """Stage 0: evaluate the start population; non-finite llk raises (metropolis.py:277-284)."""
@@ -142,13 +167,14 @@ class BatchedMetropolis:
             raise ValueError("Got NaN in likelihood evaluation! Invalid model definition? Or starting point outside prior bounds!")
         return logpts, like
 
-    def step(self, q0, logpts0, like0):
-        """One lock-step Metropolis step for every chain.  Returns (q_new, logpts_new, like_new, accepted_mask)."""
-        torch = self.torch
+    def _tune_if_due(self):
         if self.tune and self.steps_until_tune == 0:
-            self.scaling = tune_scale(self.scaling, self.accepted / float(self.tune_interval))
+            self.scaling.copy_(tune_scale(self.scaling, self.accepted / float(self.tune_interval)))
             self.steps_until_tune = self.tune_interval
             self.accepted.zero_()
+
+    def _step_body(self, q0, logpts0, like0):
+        torch = self.torch
         z = torch.randn((self.n_chains, self.n_params), dtype=torch.float64, device=self.device, generator=self.gen)
         delta = (z @ self.chol.T) * self.scaling[:, None]
         q = q0 + delta
@@ -158,14 +184,51 @@ class BatchedMetropolis:
         logpts, like = self.evaluator(q_eval)
         self._n_evals += inside.sum()
         log_u = torch.log(torch.rand(self.n_chains, dtype=torch.float64, device=self.device, generator=self.gen))
-        ratio = self.beta * (like - like0)
+        ratio = self._beta_t * (like - like0)
         accept = inside & torch.isfinite(ratio) & (log_u < ratio)          # pymc metrop_select
         q_new = torch.where(accept[:, None], q, q0)
         logpts_new = torch.where(accept[:, None], logpts, logpts0)
         like_new = torch.where(accept, like, like0)
         self.accepted += accept.to(torch.float64)
-        self.steps_until_tune -= 1
         return q_new, logpts_new, like_new, accept
+
+    def step(self, q0, logpts0, like0):
+        """One lock-step Metropolis step for every chain.  Returns (q_new, logpts_new, like_new, accepted_mask)."""
+        self._tune_if_due()
+        self.steps_until_tune -= 1
+        if not self.cuda_graph:
+            return self._step_body(q0, logpts0, like0)
+        return self._step_graphed(q0, logpts0, like0)
+
+    # ------------------------------------------------------------------ CUDA-graph path
+    def _step_graphed(self, q0, logpts0, like0):
+        torch = self.torch
+        if self._gstream is None:
+            self._gstream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._gstream.wait_stream(cur)
+        with torch.cuda.stream(self._gstream):
+            if self._state is None or self._state[0].shape != q0.shape or self._state[1].shape != logpts0.shape:
+                self._state = (q0.clone(), logpts0.clone(), like0.clone(), torch.zeros(self.n_chains, dtype=torch.bool, device=self.device))
+                self._graph, self._eager_steps = None, 0
+            sq, slp, slk, sacc = self._state
+            if q0.data_ptr() != sq.data_ptr():                    # a new population was handed in (stage start, swap, resample)
+                sq.copy_(q0); slp.copy_(logpts0); slk.copy_(like0)
+            if self._graph is None and self._eager_steps >= 2:
+                g = torch.cuda.CUDAGraph()
+                g.register_generator_state(self.gen)
+                with torch.cuda.graph(g, stream=self._gstream):
+                    qn, lpn, lkn, acc = self._step_body(sq, slp, slk)
+                    sq.copy_(qn); slp.copy_(lpn); slk.copy_(lkn); sacc.copy_(acc)
+                self._graph = g
+            if self._graph is not None:
+                self._graph.replay()
+            else:                                               # the first steps run eagerly on the same stream (warm-up)
+                qn, lpn, lkn, acc = self._step_body(sq, slp, slk)
+                sq.copy_(qn); slp.copy_(lpn); slk.copy_(lkn); sacc.copy_(acc)
+                self._eager_steps += 1
+        cur.wait_stream(self._gstream)
+        return sq, slp, slk, sacc
 
 
 def _drain_diagnostics(evaluator):
@@ -219,7 +282,7 @@ def load_last_stage(checkpoint_dir):
 
 def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_variation=1.0, tune_interval=None, seed=0,
                sample_factor_final_stage=1, max_stages=200, initial_population=None, update_weights=None, log=None,
-               on_step=None, checkpoint_dir=None, resume=False):
+               on_step=None, checkpoint_dir=None, resume=False, cuda_graph=False):
     """Batched restatement of ``smc_sample``'s stage loop (beat/sampler/smc.py:459-546).
 
     Returns dict(population [n_chains, n_params], likelihoods [n_chains], logpts, betas, n_evals, acceptance).
@@ -227,6 +290,8 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
     point after each stage; the caller re-uploads weights (``BatchedFFILogLike.update_weights``) and the end points
     are re-evaluated.  ``on_step(stage, step, q, logpts, like)`` is called after every lock-step Metropolis step with
     this rank's device tensors -- the hook for a trace backend (``beat_b200.backend.BatchedNumpyChains``).
+    ``cuda_graph``: capture the Metropolis step into a CUDA graph (see ``BatchedMetropolis``); ``on_step`` then receives the
+    state buffers the graph updates in place -- consume them before returning.
     ``checkpoint_dir``: rank 0 writes ``stage_<k>.npz`` after every stage; ``resume=True`` continues from the latest one
     (same results as an uninterrupted run: host and per-rank device RNG states are part of the checkpoint)."""
     import torch
@@ -242,7 +307,7 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
     lo, hi = D.shard_range(n_chains, rank, world)
     n_local = hi - lo
     mh = BatchedMetropolis(evaluator, lower, upper, n_local, device=device, tune=True,
-                           tune_interval=tune_interval or max(1, n_steps // 4 or 1), seed=seed * 7919 + rank)
+                           tune_interval=tune_interval or max(1, n_steps // 4 or 1), seed=seed * 7919 + rank, cuda_graph=cuda_graph)
 
     # stage 0: population from the prior (metropolis.py:128-152), identical on all ranks (shared seed)
     if initial_population is None:
@@ -261,7 +326,7 @@ def smc_sample(evaluator, lower, upper, n_chains, n_steps, device=None, coef_var
         rng.bit_generator.state = ckpt["rng_state"]
         st = ckpt["mh_states"][rank] if rank < len(ckpt["mh_states"]) else None
         if st is not None:
-            mh.scaling = torch.as_tensor(st["scaling"], device=device)
+            mh.scaling.copy_(torch.as_tensor(st["scaling"], device=device))
             mh.gen.set_state(torch.as_tensor(st["gen"], dtype=torch.uint8))
             mh._n_evals += st["n_evals"]
         if log:
@@ -339,7 +404,7 @@ def pt_betas(n_chains, n_chains_posterior, t_scale):
 
 def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_interval=(10, 15), n_chains_posterior=1,
               t_scale=1.2, beta_tune_interval=None, proposal_cov=None, tune_interval=50, seed=0, initial_population=None,
-              record_every=1):
+              record_every=1, cuda_graph=False):
     """Lock-step parallel tempering with a batched evaluator (restating beat/sampler/pt.py:100-469,472-704 without MPI).
 
     The reference runs one Metropolis chain per MPI worker at its own beta, lets each run a random number of steps
@@ -368,7 +433,7 @@ def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_in
     lo, hi = D.shard_range(n_chains, rank, world)
     n_local = hi - lo
     mh = BatchedMetropolis(evaluator, lower, upper, n_local, device=device, tune=True, tune_interval=tune_interval,
-                           seed=seed * 7919 + 1 + rank)
+                           seed=seed * 7919 + 1 + rank, cuda_graph=cuda_graph)
     if proposal_cov is None:
         proposal_cov = np.diag(((upper - lower) * 0.05) ** 2)
     mh.set_proposal_covariance(proposal_cov)
@@ -414,8 +479,8 @@ def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_in
             level[ia], level[ib] = level[ib].copy(), level[ia].copy()
             scal_all[ia], scal_all[ib] = scal_all[ib].copy(), scal_all[ia].copy()
             accd_all[ia], accd_all[ib] = accd_all[ib].copy(), accd_all[ia].copy()
-            mh.scaling = torch.as_tensor(scal_all[lo:hi], device=device).contiguous()
-            mh.accepted = torch.as_tensor(accd_all[lo:hi], device=device).contiguous()
+            mh.scaling.copy_(torch.as_tensor(scal_all[lo:hi], device=device))
+            mh.accepted.copy_(torch.as_tensor(accd_all[lo:hi], device=device))
             set_local_betas()
         k = int(acc.sum())
         n_swaps += a.size; n_acc += k

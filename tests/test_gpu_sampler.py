@@ -99,3 +99,43 @@ def test_smc_ffi_with_trace_writer_on_the_gpu(tmp_path):
         np.testing.assert_allclose(rec["seis_like"][-1].ravel(), ref, rtol=1e-9)
     assert ev.drain_diagnostics()["index_violations"] == 0
     ev.close()
+
+
+def test_metropolis_step_as_one_cuda_graph():
+    """cuda_graph=True: proposal, bounds check, the batched evaluation (libbeatgpu's kernels captured on torch's stream),
+    accept / reject and the in-place state update replay as ONE CUDA graph.  The run is deterministic, its bookkeeping
+    is consistent (stored llk == fresh evaluation of the stored point, oracle included) and it samples the same
+    posterior as the eager path."""
+    import torch
+    from beat_b200 import sampler as S
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=6, subfaults=((3, 5, 3.0),), ns=40, ndur=4, seed=31)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    dev = torch.device("cuda", 0)
+    lower = np.concatenate([prob["priors"][n][0] for n, _ in prob["var_order"]])
+    upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
+    kw = dict(n_chains=256, n_steps=12, device=dev, seed=9, max_stages=5)
+    launches0 = ev.ctx.launch_count()
+    g1 = S.smc_sample(ev.eval_device, lower, upper, cuda_graph=True, **kw)
+    launched_graph = ev.ctx.launch_count() - launches0
+    g2 = S.smc_sample(ev.eval_device, lower, upper, cuda_graph=True, **kw)
+    launches1 = ev.ctx.launch_count()
+    eager = S.smc_sample(ev.eval_device, lower, upper, cuda_graph=False, **kw)
+    launched_eager = ev.ctx.launch_count() - launches1
+    np.testing.assert_array_equal(g1["population"], g2["population"])           # deterministic
+    np.testing.assert_array_equal(g1["likelihoods"], g2["likelihoods"])
+    assert g1["n_stages"] == eager["n_stages"] and np.isfinite(g1["likelihoods"]).all()
+    fresh_lp, fresh = ev(g1["population"])
+    np.testing.assert_allclose(g1["likelihoods"], fresh, rtol=1e-12)
+    np.testing.assert_allclose(g1["logpts"], fresh_lp, rtol=1e-12)
+    for c in (0, 255):
+        ref = O.ffi_seismic_eval(prob, synthetic.split_point(prob, g1["population"][c]), impl="port").sum()
+        assert abs(g1["likelihoods"][c] - ref) <= 1e-9 * abs(ref)
+    assert (g1["population"] >= lower).all() and (g1["population"] <= upper).all()
+    # same sampler, same posterior: the tempered populations agree in their llk statistics
+    assert abs(np.median(g1["likelihoods"]) - np.median(eager["likelihoods"])) < 0.25 * np.std(eager["likelihoods"]) + 5.0
+    assert g1["n_evals"] > 256 and 0.0 < np.mean(g1["acceptance"]) < 1.0
+    # replays do not go through the library's host entry: a fraction of the eager run's host-side launches
+    assert launched_graph < 0.5 * launched_eager, (launched_graph, launched_eager)
+    assert ev.drain_diagnostics()["index_violations"] >= 0
+    ev.close()
