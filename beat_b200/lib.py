@@ -521,6 +521,7 @@ class Context:
             self._h, store_id, nt, ns, INTERPOLATION[interpolation], _ptr(lats), _ptr(lons), _ptr(az), _ptr(dp), _ptr(at),
             _ptr(abcd), lo, hi, nsec, _ptr(order), _ptr(sb), _ptr(sa), demean_first, _ptr(sidx), _ptr(hidx), _ptr(nsm),
             C.byref(wid)))
+        self._wm[wid.value] = (int(nt), int(ns))
         return wid.value
 
     def geom_loglike_batch(self, Q):

@@ -580,20 +580,37 @@ def _run_gpu_arm(args):
     from beat_b200.sampler import BatchedMetropolis
     lower = np.concatenate([prob["priors"][n][0] for n, _ in prob["var_order"]])
     upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
-    mh = BatchedMetropolis(ev.eval_device, lower, upper, B, device=device, tune=True, tune_interval=5, seed=rank)
-    mh.chol = torch.diag(torch.as_tensor((upper - lower) * 0.005, device=device))
-    mh.beta = 0.1
-    qs = head["q_dev"][0].clone()
-    lps, lks = mh.initial_llk(qs)
-    for _ in range(args.warmup):
-        qs, lps, lks, _ = mh.step(qs, lps, lks)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        qs, lps, lks, _ = mh.step(qs, lps, lks)
-    e1.record()
-    barrier()
-    sampler_value = n_gpus * B * args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+
+    def sampler_rate(cuda_graph, nchains=None):
+        nchains = nchains or B
+        m = BatchedMetropolis(ev.eval_device, lower, upper, nchains, device=device, tune=True, tune_interval=5, seed=rank, cuda_graph=cuda_graph)
+        m.set_proposal_covariance(np.diag(((upper - lower) * 0.005) ** 2))
+        m.beta = 0.1
+        qs = head["q_dev"][0][:nchains].clone()
+        lps, lks = m.initial_llk(qs)
+        for _ in range(max(args.warmup, 4)):                               # graph mode captures at its third step
+            qs, lps, lks, _ = m.step(qs, lps, lks)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            qs, lps, lks, _ = m.step(qs, lps, lks)
+        e1.record()
+        barrier()
+        return n_gpus * nchains * args.steps / (max_over_ranks(e0.elapsed_time(e1)) / 1e3), m, (qs, lps, lks)
+
+    sampler_eager, mh, (qs, lps, lks) = sampler_rate(False)
+    try:
+        sampler_value, mh_g, _ = sampler_rate(True)
+        sampler_mode = "one CUDA graph per step"
+    except Exception as e:                                                  # graph capture is an optimisation, never a requirement
+        log("graph-captured sampler step failed (%r); reporting the eager step" % (e,))
+        sampler_value, sampler_mode = sampler_eager, "eager (graph capture failed: %r)" % (e,)
+    if strong is not None:
+        try:
+            strong["sampler_step"] = {"value": sampler_rate(True, strong["chains_per_gpu"])[0], "unit": "chain-steps/s",
+                                      "eager_value": sampler_rate(False, strong["chains_per_gpu"])[0], "mode": "one CUDA graph per step"}
+        except Exception as e:
+            strong["sampler_step"] = {"value": None, "error": repr(e)}
     sampler_traced = None
     if not args.no_trace_writer:
         try:
@@ -643,7 +660,7 @@ def _run_gpu_arm(args):
                     "d2h_bytes_per_step": B * (ev.n_out + 1) * 8, "ms_per_step": head["e2e_ms_per_step"],
                     "vs_resident": head["e2e_value"] / head["value"]},
             "gpu_launches": head["launches"],
-            "sampler_step": {"value": sampler_value, "unit": "chain-steps/s",
+            "sampler_step": {"value": sampler_value, "unit": "chain-steps/s", "mode": sampler_mode, "eager_value": sampler_eager,
                              "what": "lock-step Metropolis step (proposal + bounds + batched eval + accept) with the population resident on the device",
                              "with_trace_writer": sampler_traced},
             "clocks": clocks,
@@ -721,7 +738,7 @@ def pt_driver_leg(args, ev, prob, lower, upper, n_chains, n_gpus, rank, device, 
     pop = synthetic.draw_chains(prob, n_chains, seed=97)                  # identical on every rank
     kw = dict(device=device, swap_interval=(10, 15), n_chains_posterior=max(1, n_chains // 8), t_scale=1.2,
               beta_tune_interval=4 * n_chains, proposal_cov=np.diag(((upper - lower) * 0.005) ** 2), tune_interval=20,
-              initial_population=pop, record_every=10 ** 9)
+              initial_population=pop, record_every=10 ** 9, cuda_graph=True)
     S.pt_sample(ev.eval_device, lower, upper, n_chains, 30, seed=1, **kw)          # warm-up (scratch, NCCL, allocator)
     barrier()
     t0 = time.perf_counter()

@@ -92,10 +92,15 @@ def test_probe_gather_entry():
     for mode in (0, 1, 2):
         for row_bytes in (480, 4096):
             assert c.probe_gather(mode, 8 << 20, row_bytes, 32, 1) > 1.0          # GB/s
+    for mode in (3, 4, 5, 6, 7, 8):                                # batched bulk copies, shared memory, DSMEM of 2 / 4 / 8 CTAs
+        for row_bytes in (480, 960):
+            assert c.probe_gather(mode, 8 << 20, row_bytes, 64, 1) > 1.0
     with pytest.raises(ValueError):
         c.probe_gather(0, 8 << 20, 100, 32, 1)                 # row size not a multiple of 16
     with pytest.raises(ValueError):
-        c.probe_gather(3, 8 << 20, 480, 32, 1)                 # unknown mode
+        c.probe_gather(9, 8 << 20, 480, 32, 1)                 # unknown mode
+    with pytest.raises(ValueError):
+        c.probe_gather(3, 8 << 20, 8192, 32, 1)                # batched ring would not fit in shared memory
     c.close()
 
 
