@@ -423,7 +423,7 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
     int rc;
     const bool dense_gemm = a.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && a.B >= 32;
     if (dense_gemm) {       // scratch first: ensure_tmp may free + allocate (implicitly synchronising)
-        const int mt = (a.ns + kGemmTile - 1) / kGemmTile;
+        const int mt = (a.ns + kGemmBM - 1) / kGemmBM;
         if ((rc = ensure_tmp(ctx, 4, (size_t)a.nt * a.B * a.ns * sizeof(double)))) return rc;
         if ((rc = ensure_tmp(ctx, 5, (size_t)a.nt * a.B * mt * sizeof(double)))) return rc;
     }
@@ -434,7 +434,7 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
     if (rc) return rc;
     if (dense_gemm) {
         // full (non-Toeplitz) covariance: |U_t r|^2 for all chains is a GEMM per target -> FP64 tensor cores
-        const int mt = (a.ns + kGemmTile - 1) / kGemmTile;
+        const int mt = (a.ns + kGemmBM - 1) / kGemmBM;
         double* R = (double*)ctx->d_tmp[4];
         double* qpart = (double*)ctx->d_tmp[5];
         residual_from_partials_kernel<<<(unsigned)((long)a.nt * a.B), 128, 0, ctx->stream>>>(ctx->d_partial, a.data, R, a.B, a.nt, a.ns, ca.nchunk);
@@ -446,9 +446,7 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
         g.B[0] = R; g.b_sk = 1; g.b_sn[0] = a.ns; g.b_batch = (long)a.B * a.ns;          // R_t(k, c) = R[t][c][k]
         g.upper = a.dense_upper;
         g.qpart = qpart; g.n_mtiles = mt; g.q_batch = (long)a.B * mt;
-        dim3 grid((a.B + kGemmTile - 1) / kGemmTile, mt, a.nt);
-        dgemm_tile_kernel<1><<<grid, kGemmThreads, 0, ctx->stream>>>(g);
-        CKL();
+        CK(launch_dgemm<1>(g, a.nt, ctx->stream)); ctx->n_launches++;
         SeisFinishArgs f;
         memset(&f, 0, sizeof(f));
         f.B = a.B; f.nt = a.nt; f.n_mtiles = mt; f.qpart = qpart;
@@ -1164,7 +1162,7 @@ static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* 
     if (logpts_sc < 0) logpts_sc = w.nt;
     if (w.misfit_mode == MISFIT_DENSE && ctx->geo_mode == 1 && B >= 32) {
         // dense weights: Z_t = U_t R_t for all chains on the FP64 tensor cores, straight from the caller's layout
-        const int mt = (w.ns + kGemmTile - 1) / kGemmTile;
+        const int mt = (w.ns + kGemmBM - 1) / kGemmBM;
         if ((rc = ensure_tmp(ctx, 5, (size_t)w.nt * B * mt * sizeof(double)))) return rc;
         GemmArgs g;
         memset(&g, 0, sizeof(g));
@@ -1173,9 +1171,7 @@ static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* 
         g.B[0] = d_resid; g.b_sk = 1; g.b_sn[0] = (long)w.nt * w.ns; g.b_batch = w.ns;   // resid[c][t][k]
         g.upper = w.dense_upper;
         g.qpart = (double*)ctx->d_tmp[5]; g.n_mtiles = mt; g.q_batch = (long)B * mt;
-        dim3 grid((B + kGemmTile - 1) / kGemmTile, mt, w.nt);
-        dgemm_tile_kernel<1><<<grid, kGemmThreads, 0, ctx->stream>>>(g);
-        CKL();
+        CK(launch_dgemm<1>(g, w.nt, ctx->stream)); ctx->n_launches++;
         SeisFinishArgs f;
         memset(&f, 0, sizeof(f));
         f.B = B; f.nt = w.nt; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];
@@ -1358,7 +1354,7 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
     if (ctx->geo.set && ctx->geo_mode == 1) {
         // batched over chains the geodetic composite is two GEMMs: FP64 tensor-core tiles (gemm.cuh)
         Geodetic& g = ctx->geo;
-        const int mt_max = (g.max_n + kGemmTile - 1) / kGemmTile;
+        const int mt_max = (g.max_n + kGemmBM - 1) / kGemmBM;
         if ((rc = ensure_tmp(ctx, 4, (size_t)B * g.nobs * sizeof(double)))) return rc;          // R [B, nobs]
         if ((rc = ensure_tmp(ctx, 5, (size_t)B * mt_max * sizeof(double)))) return rc;          // partial norms
         GemmArgs ga;
@@ -1371,12 +1367,10 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
             ga.B[v] = sl.p; ga.b_sn[v] = sl.stride;             // slip_v(k=patch, n=chain) = q[n*stride + off + k]
         }
         ga.upper = 0; ga.data = g.d_data; ga.odw = g.d_odw; ga.R = (double*)ctx->d_tmp[4]; ga.ldr = g.nobs;
-        dim3 grid1((B + kGemmTile - 1) / kGemmTile, (g.nobs + kGemmTile - 1) / kGemmTile);
-        dgemm_tile_kernel<0><<<grid1, kGemmThreads, 0, ctx->stream>>>(ga);
-        CKL();
+        CK(launch_dgemm<0>(ga, 1, ctx->stream)); ctx->n_launches++;
         for (int d = 0; d < g.nds; ++d) {
             const int n = g.hi[d] - g.lo[d];
-            const int mt = (n + kGemmTile - 1) / kGemmTile;
+            const int mt = (n + kGemmBM - 1) / kGemmBM;
             GemmArgs gb;
             memset(&gb, 0, sizeof(gb));
             gb.M = n; gb.N = B; gb.K = n; gb.n_parts = 1;
@@ -1384,9 +1378,7 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
             gb.B[0] = (const double*)ctx->d_tmp[4] + g.lo[d]; gb.b_sk = 1; gb.b_sn[0] = g.nobs;
             gb.upper = g.h_upper[d];
             gb.qpart = (double*)ctx->d_tmp[5]; gb.n_mtiles = mt;
-            dim3 grid2((B + kGemmTile - 1) / kGemmTile, mt);
-            dgemm_tile_kernel<1><<<grid2, kGemmThreads, 0, ctx->stream>>>(gb);
-            CKL();
+            CK(launch_dgemm<1>(gb, 1, ctx->stream)); ctx->n_launches++;
             GeoFinishArgs f;
             memset(&f, 0, sizeof(f));
             f.B = B; f.n_mtiles = mt; f.qpart = (const double*)ctx->d_tmp[5];

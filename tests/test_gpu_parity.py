@@ -221,7 +221,7 @@ def test_fused_loglike_vs_oracle(case, store, rtol):
 
 
 @pytest.mark.parametrize("geo_mode", ["mma", "simple"])
-@pytest.mark.parametrize("nobs,B", [([60, 45], 16), ([150, 70, 5], 70), ([64], 129)])
+@pytest.mark.parametrize("nobs,B", [([60, 45], 16), ([150, 70, 5], 70), ([64], 129), ([260, 131], 150)])
 def test_fused_joint_geodetic_laplacian(geo_mode, nobs, B, monkeypatch):
     """Config-4 shape: seismic + geodetic static (dense non-Toeplitz C) + laplacian prior, all in one call.
     geo_mode "mma" = FP64 tensor-core GEMM tiles over all chains, "simple" = one CTA per (chain, dataset)."""
@@ -496,7 +496,7 @@ def test_eval_device_is_stream_ordered_with_torch():
 
 
 @pytest.mark.parametrize("mode", ["mma", "simple"])
-@pytest.mark.parametrize("ns,B", [(130, 70), (40, 33), (64, 128)])
+@pytest.mark.parametrize("ns,B", [(130, 70), (40, 33), (64, 128), (125, 70), (301, 96)])     # even / odd trace lengths: 16- and 8-byte staging copies
 def test_dense_covariance_misfit_gemm_path(mode, ns, B, monkeypatch):
     """Full non-Toeplitz covariance (dense upper-triangular U): in the chunked path |U r|^2 of all chains is a batched
     FP64 tensor-core GEMM per target ("mma") or one matvec per (chain, target) ("simple"); both equal the oracle."""
