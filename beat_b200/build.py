@@ -39,6 +39,16 @@ def source_hash():
     return h.hexdigest()[:16]
 
 
+def kernel_hash(files=("stack.cuh",)):
+    """sha256 (16 hex digits) over the kernel sources a committed ncu traffic record belongs to (bench.py matches it,
+    together with the L2 blocking the capture ran with, before reporting `roofline.traffic`)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in files:
+        h.update(open(os.path.join(HERE, "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def build(force=False, verbose=False, extra_flags=()):
     if not force and up_to_date():
         return OUT

@@ -161,6 +161,8 @@ struct beatgpu_ctx {
     beatgpu_geom_layout glayout;
     double* d_gfixed = nullptr;
     double ev_lat = 0, ev_lon = 0, stf_anchor = -1.0;
+    int stf_type = BEATGPU_STF_HALFSINUSOID, off_peak_ratio = -1;   // beatgpu_geom_set_stf
+    double* d_peak_ratio = nullptr;                                 // fixed TriangularSTF.peak_ratio (one value)
     void *d_rplan = nullptr, *d_cplan = nullptr, *d_rawT = nullptr, *d_gmean = nullptr;
     size_t g_rplan_bytes = 0, g_cplan_bytes = 0, g_raw_bytes = 0, g_mean_bytes = 0;
     unsigned int* d_gerr = nullptr;
@@ -609,7 +611,7 @@ void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
         cudaFree(g.d_tgt_of); cudaFree(g.d_tgt_f); cudaFree(g.d_tgt_nraw); cudaFree(g.d_tgt_ibeg); cudaFree(g.d_taper);
         cudaFree(g.d_rcv_arrival); cudaFree(g.d_tgt_arrival); cudaFree(g.d_rcv_station); cudaFree(g.d_tgt_station); cudaFree(g.d_tgt_rcv);
     }
-    cudaFree(ctx->d_gfixed); cudaFree(ctx->d_rplan); cudaFree(ctx->d_cplan); cudaFree(ctx->d_rawT); cudaFree(ctx->d_gmean);
+    cudaFree(ctx->d_gfixed); cudaFree(ctx->d_peak_ratio); cudaFree(ctx->d_rplan); cudaFree(ctx->d_cplan); cudaFree(ctx->d_rawT); cudaFree(ctx->d_gmean);
     cudaFree(ctx->d_gerr);
     for (auto e : ctx->tev) if (e) cudaEventDestroy(e);
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
@@ -1409,7 +1411,28 @@ int beatgpu_ffi_loglike_batch_dev(beatgpu_ctx* ctx, int B, const double* q, doub
         CKL();
     }
 
-    if (ctx->lap.set) {
+    if (ctx->lap.set && ctx->geo_mode == 1 && B >= 32) {
+        // batched over chains |L u_v|^2 is a GEMM per slip variable with a column-norm epilogue: FP64 tensor-core tiles
+        const int np = ctx->np_total, mt = (np + kGemmBM - 1) / kGemmBM;
+        if ((rc = ensure_tmp(ctx, 5, (size_t)L.n_slipvars * B * mt * sizeof(double)))) return rc;
+        for (int v = 0; v < L.n_slipvars; ++v) {
+            GemmArgs gl;
+            memset(&gl, 0, sizeof(gl));
+            gl.M = np; gl.N = B; gl.K = np; gl.n_parts = 1;
+            gl.A[0] = ctx->lap.d_LT; gl.a_sm = 1; gl.a_sk = np;                       // L(m, k) = LT[k*np + m]
+            VarRef sl = var_ref(ctx, q, L.off_slip[v], ctx->canon_slip[v]);
+            gl.B[0] = sl.p; gl.b_sk = 1; gl.b_sn[0] = sl.stride;
+            gl.qpart = (double*)ctx->d_tmp[5] + (size_t)v * B * mt; gl.n_mtiles = mt;
+            CK(launch_dgemm<1>(gl, 1, ctx->stream)); ctx->n_launches++;
+        }
+        LapFinishArgs f;
+        memset(&f, 0, sizeof(f));
+        f.B = B; f.n_mtiles = mt; f.nvar = L.n_slipvars; f.np = np; f.qpart = (const double*)ctx->d_tmp[5];
+        f.sdet = ctx->lap.sdet; f.hyper_idx = ctx->lap.hyper_idx; f.hyp = hyp.p; f.hyp_sc = hyp.stride;
+        f.logpts = logpts; f.logpts_sc = n_out; f.out_col = ctx->lap.out_ofs;
+        laplacian_finish_kernel<<<(B + 127) / 128, 128, 0, ctx->stream>>>(f);
+        CKL();
+    } else if (ctx->lap.set) {
         LapArgs a;
         memset(&a, 0, sizeof(a));
         a.B = B; a.np = ctx->np_total; a.nvar = L.n_slipvars;

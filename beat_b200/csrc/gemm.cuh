@@ -139,15 +139,17 @@ __global__ void __launch_bounds__(kGemmThreads, 2) dgemm_tile_kernel(GemmArgs g)
                     a[blk][kp] = *reinterpret_cast<const double2*>(As + (kk + 2 * tig + kp) * kGemmLDA + wm + blk * 16 + 2 * gid);
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(Bs + (wn + j * 8 + gid) * kGemmLDB + kk + 2 * tig);
+            // all 16 products of one k set, then the 16 of the other: consecutive DMMAs never touch the same accumulator
 #pragma unroll
-            for (int blk = 0; blk < 2; ++blk)
+            for (int kp = 0; kp < 2; ++kp)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dmma_m8n8k4(acc[blk * 2 + 0][j][0], acc[blk * 2 + 0][j][1], a[blk][0].x, b[j].x);
-                    dmma_m8n8k4(acc[blk * 2 + 1][j][0], acc[blk * 2 + 1][j][1], a[blk][0].y, b[j].x);
-                    dmma_m8n8k4(acc[blk * 2 + 0][j][0], acc[blk * 2 + 0][j][1], a[blk][1].x, b[j].y);
-                    dmma_m8n8k4(acc[blk * 2 + 1][j][0], acc[blk * 2 + 1][j][1], a[blk][1].y, b[j].y);
-                }
+                for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double bk = kp ? b[j].y : b[j].x;
+                        dmma_m8n8k4(acc[blk * 2 + 0][j][0], acc[blk * 2 + 0][j][1], a[blk][kp].x, bk);
+                        dmma_m8n8k4(acc[blk * 2 + 1][j][0], acc[blk * 2 + 1][j][1], a[blk][kp].y, bk);
+                    }
         }
     }
     cp_async_wait<0>();
@@ -226,6 +228,30 @@ __global__ void geodetic_finish_kernel(GeoFinishArgs a)
     const double M = (double)(short)a.nsamp;
     const double norm = M * (2.0 * hp + 1.8378770664093453);
     a.logpts[(long)c * a.logpts_sc + a.out_col] = (-0.5) * (a.slog_pdet + norm + (1.0 / exp(hp * 2.0)) * quad);
+}
+
+// Laplacian prior from the per-row-tile partial norms of Z_v = L u_v (one GEMM per slip variable, epilogue 1):
+// sum over slip vars of -1/2 ( -sdet + np (log 2pi + 2h) + exp(-2h) |L u_v|^2 )   (beat/models/laplacian.py:88-96,128-139)
+struct LapFinishArgs {
+    int B, n_mtiles, nvar, np;
+    const double* qpart;                  // [nvar, B, n_mtiles]
+    double sdet; int hyper_idx;
+    const double* hyp; long hyp_sc;
+    double* logpts; long logpts_sc; int out_col;
+};
+
+__global__ void laplacian_finish_kernel(LapFinishArgs a)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.B) return;
+    const double hp = a.hyp[(long)c * a.hyp_sc + a.hyper_idx];
+    double total = 0.0;
+    for (int v = 0; v < a.nvar; ++v) {
+        double e = 0.0;
+        for (int j = 0; j < a.n_mtiles; ++j) e += a.qpart[((long)v * a.B + c) * a.n_mtiles + j];
+        total += (-0.5) * (-a.sdet + ((double)a.np * (1.8378770664093453 + 2.0 * hp)) + (1.0 / exp(hp * 2.0) * e));
+    }
+    a.logpts[(long)c * a.logpts_sc + a.out_col] = total;
 }
 
 // ---------------------------------------------------------------------------------------------------------

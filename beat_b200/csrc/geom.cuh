@@ -77,6 +77,8 @@ struct GeomPlanArgs {
     int B, nr;
     ChainVar east, north, depth, strike, dip, rake, magnitude, time, duration;     // km, km, km, deg, deg, deg, Mw, s, s
     double ev_lat, ev_lon, stf_anchor;
+    int stf_type;                                                                   // BEATGPU_STF_*
+    ChainVar peak_ratio;                                                            // TriangularSTF.peak_ratio
     const double* rcv_lat; const double* rcv_lon;                                   // [nr]
     GeomStoreDev store;
     int interpolation;
@@ -159,30 +161,66 @@ __global__ void __launch_bounds__(128) geom_plan_kernel(GeomPlanArgs a)
         ChainPlan cp;
         const double tref = a.time.p[(long)c * a.time.stride], dur = a.duration.p[(long)c * a.duration.stride];
         const double dt = a.store.deltat;
-        const double tmin_stf = tref - dur * (a.stf_anchor + 1.0) * 0.5, tmax_stf = tref + dur * (1.0 - a.stf_anchor) * 0.5;
+        // [pyrocko] {HalfSinusoid,Boxcar,Triangular}STF.discretize_t: support [tmin_stf, tmax_stf], grid points
+        // round(t/dt)*dt, amplitudes = integrals of the shape over the sampling intervals centred on the grid, normalised
+        double tmin_stf, tmax_stf, t_peak = 0.0;
+        if (a.stf_type == BEATGPU_STF_TRIANGULAR) {
+            const double ra = a.peak_ratio.p[(long)c * a.peak_ratio.stride], rb = 1.0 - ra;
+            const double ca = ra + (rb * rb / 3.0 - ra * ra / 3.0) / (ra + rb), cb = 1.0 - ca;        // centroid_ratio
+            if (a.stf_anchor <= 0.0) { tmin_stf = tref - ca * dur * (a.stf_anchor + 1.0); tmax_stf = tmin_stf + dur; }
+            else                     { tmax_stf = tref + cb * dur * (1.0 - a.stf_anchor); tmin_stf = tmax_stf - dur; }
+            t_peak = tmin_stf + dur * ra;
+            if (!(ra >= 0.0 && ra <= 1.0)) bad = true;
+        } else {
+            tmin_stf = tref - dur * (a.stf_anchor + 1.0) * 0.5; tmax_stf = tref + dur * (1.0 - a.stf_anchor) * 0.5;
+        }
         const double g0 = rint(tmin_stf / dt), g1 = rint(tmax_stf / dt);
         const double tmin = g0 * dt, tmax = g1 * dt;
         const double nf = rint((tmax - tmin) / dt) + 1.0;
         int n = 1;
-        if (!(isfinite(tref) && isfinite(dur)) || !(nf >= 1.0) || nf > (double)kGeomMaxStf) bad = true;
+        // the boxcar's centroid shift may add one point
+        if (!(isfinite(tref) && isfinite(dur)) || !(nf >= 1.0) || nf > (double)(kGeomMaxStf - (a.stf_type == BEATGPU_STF_BOXCAR ? 1 : 0))) bad = true;
         else n = (int)nf;
-        cp.id0 = bad ? 0 : (int)g0;
-        cp.n_stf = n;
-        cp.pad0 = cp.pad1 = 0;
-        for (int k = 0; k < kGeomMaxStf; ++k) cp.amp[k] = 0.f;
+        int id0 = bad ? 0 : (int)g0;
+        double w[kGeomMaxStf + 1];
+        w[0] = 1.0;
         if (n > 1) {
             const double start = tmin - 0.5 * dt, stop = tmax + 0.5 * dt, step = (stop - start) / n;
-            double fint[kGeomMaxStf + 1], sum = 0.0;
+            double sum = 0.0, prev = 0.0;
             for (int k = 0; k <= n; ++k) {
                 const double e = (k == n) ? stop : start + k * step;                 // numpy.linspace
-                const double te = fmax(tmin_stf, fmin(tmax_stf, e));
-                fint[k] = -cos((te - tmin_stf) * (CUDART_PI / dur));
+                const double te = fmax(tmin_stf, fmin(tmax_stf, e));                  // the shapes vanish outside the support
+                double F;                                                            // antiderivative of the shape at te
+                if (a.stf_type == BEATGPU_STF_BOXCAR) F = te - tmin_stf;
+                else if (a.stf_type == BEATGPU_STF_TRIANGULAR) {
+                    if (te <= t_peak) F = (t_peak > tmin_stf) ? (te - tmin_stf) * (te - tmin_stf) / (2.0 * (t_peak - tmin_stf)) : 0.0;
+                    else F = 0.5 * (t_peak - tmin_stf) + (te - t_peak) - (te - t_peak) * (te - t_peak) / (2.0 * (tmax_stf - t_peak));
+                } else F = -cos((te - tmin_stf) * (CUDART_PI / dur));
+                if (k > 0) { w[k - 1] = F - prev; sum += w[k - 1]; }
+                prev = F;
             }
-            for (int k = 0; k < n; ++k) sum += fint[k + 1] - fint[k];
-            for (int k = 0; k < n; ++k) cp.amp[k] = (float)((fint[k + 1] - fint[k]) / sum);
-        } else {
-            cp.amp[0] = 1.f;
+            for (int k = 0; k < n; ++k) w[k] /= sum;
         }
+        if (a.stf_type == BEATGPU_STF_BOXCAR && !bad) {
+            // tshift = sum(amplitudes * times) - centroid_time; sshift(times, amplitudes, -tshift, deltat)
+            const double tstep = n > 1 ? (tmax - tmin) / (n - 1) : 0.0;
+            double cen = 0.0;
+            for (int k = 0; k < n; ++k) cen += w[k] * ((k == n - 1 && n > 1) ? tmax : tmin + k * tstep);
+            const double sft = -(cen - (tref - 0.5 * dur * a.stf_anchor));
+            const double t0 = floor(sft / dt) * dt, t1 = ceil(sft / dt) * dt;
+            if (t0 != t1) {
+                const double wl = (t1 - sft) / dt, wr = (sft - t0) / dt;
+                w[n] = 0.0;
+                for (int k = n; k >= 1; --k) w[k] = wl * w[k] + wr * w[k - 1];
+                w[0] = wl * w[0];
+                n += 1;
+                id0 = (int)rint((tmin + t0) / dt);
+            }
+        }
+        cp.id0 = bad ? 0 : id0;
+        cp.n_stf = n;
+        cp.pad0 = cp.pad1 = 0;
+        for (int k = 0; k < kGeomMaxStf; ++k) cp.amp[k] = (k < n) ? (float)w[k] : 0.f;
         a.cplan[c] = cp;
     }
 

@@ -134,6 +134,9 @@ class BatchedGeometryLogLike:
         ctx.geom_set_source(_layout_from_offsets(gprob["offsets"], gprob["n_params"], gprob["n_hypers"],
                                                  gprob.get("n_time_shifts", 0), gprob.get("n_sources", 1)), fixed,
                             gprob["event"]["lat"], gprob["event"]["lon"], gprob.get("stf_anchor", -1.0))
+        if gprob.get("stf_type", "HalfSinusoid") != "HalfSinusoid":
+            ctx.geom_set_stf(gprob["stf_type"], gprob.get("stf_anchor", -1.0), gprob["offsets"].get("peak_ratio", -1),
+                             gprob.get("peak_ratio", 0.5))
         self.store_id = ctx.geom_upload_store(st["traces"], st["itmin"], st["nsamples"], st["z0"], st["dz"], st["x0"], st["dx"],
                                               st["deltat"])
         self.n_params = gprob["n_params"]
@@ -237,7 +240,8 @@ class SeisSynthesizer(_OpBase):
                  "station_corrections")
 
     def __init__(self, store, event, targets, arrival_taper, arrival_times, filterer, pre_stack_cut=True,
-                 station_corrections=False, interpolation="multilinear", stf_anchor=-1.0, chop_bounds=("b", "c"), device=0):
+                 station_corrections=False, interpolation="multilinear", stf_anchor=-1.0, chop_bounds=("b", "c"), device=0,
+                 stf_type="HalfSinusoid"):
         if not pre_stack_cut:
             raise NotImplementedError("only pre_stack_cut=True (the reference's default) is implemented")
         self.store, self.event, self.targets = store, event, targets
@@ -255,9 +259,16 @@ class SeisSynthesizer(_OpBase):
         if self.station_corrections:            # the Op receives one time_shift per target (pytensorf.py:248-252)
             offsets["time_shifts"], n_ts = n_par, self.nt
             n_par += n_ts
+        self.stf_type = stf_type
+        if stf_type == "Triangular":            # the triangle's `peak_ratio` is one more (optional) named input; 0.5 when absent
+            offsets["peak_ratio"] = n_par
+            n_par += 1
+        self._off_peak = offsets.get("peak_ratio", -1)
         self._n_par = n_par
         self._ctx = Context(device)
         self._ctx.geom_set_source(_layout_from_offsets(offsets, n_par, 0, n_ts), None, event["lat"], event["lon"], stf_anchor)
+        if stf_type != "HalfSinusoid":
+            self._ctx.geom_set_stf(stf_type, stf_anchor, self._off_peak)
         sid = self._ctx.geom_upload_store(store["traces"], store["itmin"], store["nsamples"], store["z0"], store["dz"],
                                           store["x0"], store["dx"], store["deltat"])
         self._wid = self._ctx.geom_add_wavemap(sid, self.ns, interpolation, targets["lats"], targets["lons"], targets["azimuths"],
@@ -272,10 +283,13 @@ class SeisSynthesizer(_OpBase):
     def perform(self, node, inputs, output):
         point = {v: np.asarray(i, dtype=np.float64) for v, i in zip(self.varnames, inputs)}
         shifts = point.pop("time_shift", None)
+        peak = point.pop("peak_ratio", None)
         point = {v: point[v] for v in GEOM_VARS}                     # input order does not matter (pytensorf.py:133)
         B = max(p.size for p in point.values())
         batched = any(p.ndim >= 1 and p.size > 1 for p in point.values())
         Q = np.zeros((B, self._n_par))
+        if self._off_peak >= 0:
+            Q[:, self._off_peak] = 0.5 if peak is None else peak.reshape(-1)
         for i, v in enumerate(GEOM_VARS):
             Q[:, i] = point[v].reshape(-1)
         arrival = np.broadcast_to(self.arrival_times, (B, self.nt))

@@ -109,6 +109,7 @@ _SIGNATURES = {
     "beatgpu_source_hash": (C.c_char_p, []),
     "beatgpu_geom_timeouts": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "beatgpu_geom_set_source": (C.c_int, [_P, C.POINTER(GeomLayout), _P, C.c_double, C.c_double, C.c_double]),
+    "beatgpu_geom_set_stf": (C.c_int, [_P, C.c_int, C.c_double, C.c_int, C.c_double]),
     "beatgpu_geom_upload_store": (C.c_int, [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P, _P, _P,
                                             C.POINTER(C.c_int)]),
     "beatgpu_geom_add_wavemap": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int,
@@ -119,6 +120,8 @@ _SIGNATURES = {
     "beatgpu_probe_gather": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double)]),
 }
+
+STF_TYPES = {"HalfSinusoid": 0, "Boxcar": 1, "Triangular": 2}          # BEATGPU_STF_*
 
 _lib = None
 
@@ -478,6 +481,13 @@ class Context:
         self._check(self._lib.beatgpu_geom_set_source(self._h, C.byref(layout), _ptr(fx), float(event_lat), float(event_lon),
                                                       float(stf_anchor)))
         self._geom_n_params = layout.n_params
+
+    def geom_set_stf(self, stf_type, stf_anchor=-1.0, off_peak_ratio=-1, fixed_peak_ratio=0.5):
+        """stf_type: a key of the reference's stf_catalog (beat/sources.py:723-729): Boxcar, Triangular, HalfSinusoid."""
+        if stf_type not in STF_TYPES:
+            raise ValueError("stf_type %r not in %s (beat/config.py:1359-1365)" % (stf_type, sorted(STF_TYPES)))
+        self._check(self._lib.beatgpu_geom_set_stf(self._h, STF_TYPES[stf_type], float(stf_anchor), int(off_peak_ratio),
+                                                   float(fixed_peak_ratio)))
 
     def geom_upload_store(self, traces, itmin, nsamples, z0, dz, x0, dx, deltat):
         traces = np.ascontiguousarray(traces, dtype=np.float32)

@@ -251,7 +251,8 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
                           interpolation="multilinear", filterer=None, dist_range=(500e3, 700e3), shift_km=10.0,
                           depth_range_km=(2.0, 10.0), dz=2.0e3, dx=4.0e3, nrec=200, time_bounds=(-3.0, 3.0),
                           duration_bounds=(0.0, 6.0), seed=99, hp_specific=False, ragged=True, lead=10.0,
-                          station_corrections=False, corr_bounds=(-1.0, 1.0), n_sources=1):
+                          station_corrections=False, corr_bounds=(-1.0, 1.0), n_sources=1, stf_type="HalfSinusoid",
+                          sample_peak_ratio=True):
     """Synthetic geometry-mode seismic problem (one wavemap, one DC source).  ``data`` / weights are attached later by
     ``attach_geometry_data`` from synthetics of a reference point (tests: the oracle's; bench: the GPU engine's)."""
     rng = np.random.default_rng(seed)
@@ -282,6 +283,8 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
     nt = len(lats)
     n_hypers = nt if hp_specific else 1
     var_order = [(v, n_sources) for v in GEOM_VARS] + [("hypers", n_hypers)]     # pymc vectors of shape (n_sources,)
+    if stf_type == "Triangular" and sample_peak_ratio:      # TriangularSTF.peak_ratio is a sampled variable (defaults.py:238-240)
+        var_order.insert(len(GEOM_VARS), ("peak_ratio", n_sources))
     if station_corrections:                   # one hierarchical time shift per station (seismic.py:198-294)
         var_order.append(("time_shifts", n_stations))
     offsets, o = {}, 0
@@ -291,6 +294,8 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
     priors = dict(east_shift=(-shift_km, shift_km), north_shift=(-shift_km, shift_km), depth=depth_range_km,
                   strike=(0.0, 360.0), dip=(0.0, 90.0), rake=(-180.0, 180.0), magnitude=(5.5, 6.5), time=time_bounds,
                   duration=duration_bounds, hypers=(np.zeros(n_hypers), np.full(n_hypers, 4.0)))
+    if stf_type == "Triangular" and sample_peak_ratio:
+        priors["peak_ratio"] = (0.0, 1.0)
     if station_corrections:
         priors["time_shifts"] = (np.full(n_stations, corr_bounds[0]), np.full(n_stations, corr_bounds[1]))
     priors = {k: (np.atleast_1d(np.asarray(v[0], dtype=float)), np.atleast_1d(np.asarray(v[1], dtype=float))) for k, v in priors.items()}
@@ -300,7 +305,7 @@ def make_geometry_problem(n_stations=4, channels=("N", "E", "Z"), ns=40, deltat=
               hyper_idx=(np.arange(nt, dtype=np.int32) if hp_specific else np.zeros(nt, dtype=np.int32)),
               data=None, U=None, slog_pdet=None,
               station_idx=(np.repeat(np.arange(n_stations, dtype=np.int32), len(channels)) if station_corrections else None))
-    return dict(mode="geometry", store=store, event=dict(lat=ev_lat, lon=ev_lon), stf_anchor=-1.0, var_order=var_order,
+    return dict(mode="geometry", store=store, event=dict(lat=ev_lat, lon=ev_lon), stf_anchor=-1.0, stf_type=stf_type, var_order=var_order,
                 offsets=offsets, n_params=o, n_hypers=n_hypers, n_time_shifts=n_stations if station_corrections else 0,
                 n_sources=n_sources,
                 priors=priors, wavemaps=[wm], seed=seed)

@@ -701,15 +701,18 @@ def _run_gpu_arm(args):
         # DRAM traffic of the stack kernel: from the committed ncu capture ONLY if it was taken with this very build
         traffic, tnote, l2_bytes = None, None, None
         build_hash = beatlib.source_hash()
+        from beat_b200.build import kernel_hash
         tpath = os.path.join(ROOT, "profiles", "stack_kernel_traffic.json")
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
                 if (CONFIG == "c3" and NOISE == "exponential" and not args.quick and tj.get("chains") == B and tj.get("store") == args.store
-                        and tj.get("interpolation") == args.interpolation and tj.get("source_hash") == build_hash):
+                        and tj.get("interpolation") == args.interpolation and tj.get("stack_cuh_hash") == kernel_hash()
+                        and tj.get("l2_blocking") == blocking):
                     traffic, tnote, l2_bytes = tj.get("dram_bytes_per_launch"), tj.get("note"), tj.get("l2_to_sm_bytes")
                 else:
-                    tnote = "profiles/stack_kernel_traffic.json was captured on another build / configuration (source hash %s, this build %s): traffic withheld" % (tj.get("source_hash"), build_hash)
+                    tnote = ("profiles/stack_kernel_traffic.json was captured on another kernel source / configuration (stack.cuh %s, blocking %s; "
+                             "this run %s, %s): traffic withheld" % (tj.get("stack_cuh_hash"), tj.get("l2_blocking"), kernel_hash(), blocking))
             except Exception:
                 pass
         n_sm, dev_name = ev.ctx.device_info()

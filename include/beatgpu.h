@@ -259,7 +259,7 @@ const char* beatgpu_source_hash(void);
  * SeismicGeometryComposite.get_formula (beat/models/seismic.py:737-837).  The synthesis itself is pyrocko's
  * (un-vendored dependency, >= 2023.10.11): its published algorithm is restated, see csrc/geom.cuh and
  * oracle/geom_oracle.py.  Times are relative to the reference event's origin time.  Supported: DC sources (one or
- * several, stacked), HalfSinusoid STF, GF component scheme 'elastic10', store type A (source depth x distance), pre_stack_cut
+ * several, stacked), HalfSinusoid / Boxcar / Triangular STF, GF component scheme 'elastic10', store type A (source depth x distance), pre_stack_cut
  * = True (the reference's default), time domain, station corrections.  A context is either finite-fault or
  * geometry mode.                                                                                            */
 
@@ -283,6 +283,18 @@ typedef struct beatgpu_geom_layout {
  * stf_anchor: HalfSinusoidSTF.anchor, -1 in the reference (beat/config.py:2060).                             */
 int beatgpu_geom_set_source(beatgpu_ctx* ctx, const beatgpu_geom_layout* layout, const double* fixed,
                             double event_lat, double event_lon, double stf_anchor);
+
+/* Source time function of the geometry-mode sources.  BEAT offers pyrocko's Boxcar, Triangular and HalfSinusoid STFs
+ * (stf_catalog, beat/sources.py:723-729; SeismicGeometryConfig.stf_type, beat/config.py:1359-1365, default
+ * HalfSinusoid), creates them with anchor = -1 (beat/config.py:2058-2060) and routes the sampled `duration` -- and
+ * `peak_ratio` of the triangle (bounds beat/defaults.py:238-240) -- to them (utility.update_source, :773-797).
+ * off_peak_ratio: column of q holding peak_ratio (a block of n_sources values) or -1 = fixed_peak_ratio for every chain;
+ * ignored unless stf_type is BEATGPU_STF_TRIANGULAR.  Call after beatgpu_geom_set_source (which resets the STF to
+ * HalfSinusoid with the anchor given there).                                                                  */
+#define BEATGPU_STF_HALFSINUSOID 0
+#define BEATGPU_STF_BOXCAR       1
+#define BEATGPU_STF_TRIANGULAR   2
+int beatgpu_geom_set_stf(beatgpu_ctx* ctx, int stf_type, double stf_anchor, int off_peak_ratio, double fixed_peak_ratio);
 
 /* Upload a GF store (what engine.get_store(target.store_id) opens in the reference, beat/heart.py:3657): dims =
  * (n_source_depths, n_distances, 10, row_length); record (iz, ix, g) holds nsamples[iz,ix,g] <= row_length float32

@@ -130,6 +130,122 @@ def halfsinusoid_discretize_t(duration, anchor, deltat, tref):
     return times, amplitudes
 
 
+def plf_integrate_piecewise(x_edges, x, y):
+    """[pyrocko] util.plf_integrate_piecewise: integrals over the bins [x_edges[k], x_edges[k+1]] of the piecewise-linear
+    function through (x, y), continued by its end values.  Restated as the exact integral: bin by bin, the trapezoids
+    between the breakpoints falling inside the bin (a jump -- two breakpoints with the same x -- contributes nothing)."""
+    x_edges, x, y = (np.asarray(v, dtype=np.float64) for v in (x_edges, x, y))
+    out = np.zeros(x_edges.size - 1)
+    for k in range(out.size):
+        lo, hi = x_edges[k], x_edges[k + 1]
+        inner = [(xi, i) for i, xi in enumerate(x) if lo < xi < hi]
+        px = [lo] + [xi for xi, _ in inner] + [hi]
+        # value at the bin edges: np.interp semantics (right-continuous at a jump is immaterial for the integral
+        # unless the edge sits exactly on it, where the one-sided limits towards the bin interior are what counts)
+        def left_limit(t):
+            i = np.searchsorted(x, t, side="left")            # first breakpoint >= t
+            if i == 0:
+                return y[0]
+            if i == x.size:
+                return y[-1]
+            return y[i - 1] + (y[i] - y[i - 1]) * (t - x[i - 1]) / (x[i] - x[i - 1]) if x[i] > x[i - 1] else y[i - 1]
+
+        def right_limit(t):
+            i = np.searchsorted(x, t, side="right")           # first breakpoint > t
+            if i == 0:
+                return y[0]
+            if i == x.size:
+                return y[-1]
+            return y[i - 1] + (y[i] - y[i - 1]) * (t - x[i - 1]) / (x[i] - x[i - 1]) if x[i] > x[i - 1] else y[i]
+        tot = 0.0
+        for j in range(len(px) - 1):
+            tot += 0.5 * (right_limit(px[j]) + left_limit(px[j + 1])) * (px[j + 1] - px[j])
+        out[k] = tot
+    return out
+
+
+def sshift(times, amplitudes, tshift, deltat):
+    """[pyrocko] gf.seismosizer.sshift: move a discretised STF by a sub-sample amount (linear split between the two
+    neighbouring grid points: one point more); a shift that is a whole number of samples leaves the arrays untouched."""
+    t0 = math.floor(tshift / deltat) * deltat
+    t1 = math.ceil(tshift / deltat) * deltat
+    if t0 == t1:
+        return times, amplitudes
+    amplitudes2 = np.zeros(amplitudes.size + 1)
+    amplitudes2[:-1] += (t1 - tshift) / deltat * amplitudes
+    amplitudes2[1:] += (tshift - t0) / deltat * amplitudes
+    times2 = np.arange(times.size + 1, dtype=np.float64) * deltat + times[0] + t0
+    return times2, amplitudes2
+
+
+def boxcar_discretize_t(duration, anchor, deltat, tref):
+    """[pyrocko] gf.seismosizer.BoxcarSTF.discretize_t: bin integrals of the boxcar on the store's time grid, then a
+    sub-sample shift so that the discrete centroid equals ``centroid_time = tref - duration * anchor / 2``."""
+    tmin_stf = tref - duration * (anchor + 1.0) * 0.5
+    tmax_stf = tref + duration * (1.0 - anchor) * 0.5
+    tmin = py_round(tmin_stf / deltat) * deltat
+    tmax = py_round(tmax_stf / deltat) * deltat
+    nt = int(py_round((tmax - tmin) / deltat)) + 1
+    times = np.linspace(tmin, tmax, nt)
+    amplitudes = np.ones_like(times)
+    if times.size > 1:
+        t_edges = np.linspace(tmin - 0.5 * deltat, tmax + 0.5 * deltat, nt + 1)
+        t = tmin_stf + duration * np.array([0.0, 0.0, 1.0, 1.0])
+        f = np.array([0.0, 1.0, 1.0, 0.0])
+        amplitudes = plf_integrate_piecewise(t_edges, t, f)
+        amplitudes /= np.sum(amplitudes)
+    tshift = np.sum(amplitudes * times) - (tref - 0.5 * duration * anchor)
+    return sshift(times, amplitudes, -tshift, deltat)
+
+
+def triangular_centroid_ratio(peak_ratio):
+    """[pyrocko] TriangularSTF.centroid_ratio."""
+    ra = peak_ratio
+    rb = 1.0 - ra
+    return ra + (rb ** 2 / 3.0 - ra ** 2 / 3.0) / (ra + rb)
+
+
+def triangular_discretize_t(duration, peak_ratio, anchor, deltat, tref):
+    """[pyrocko] gf.seismosizer.TriangularSTF.discretize_t (+ tminmax_stf): a triangle of base ``duration`` whose apex sits
+    at ``peak_ratio`` of the base, anchored through its centroid; bin integrals on the store's time grid."""
+    ca = triangular_centroid_ratio(peak_ratio)
+    cb = 1.0 - ca
+    if anchor <= 0.0:
+        tmin_stf = tref - ca * duration * (anchor + 1.0)
+        tmax_stf = tmin_stf + duration
+    else:
+        tmax_stf = tref + cb * duration * (1.0 - anchor)
+        tmin_stf = tmax_stf - duration
+    tmin = py_round(tmin_stf / deltat) * deltat
+    tmax = py_round(tmax_stf / deltat) * deltat
+    nt = int(py_round((tmax - tmin) / deltat)) + 1
+    if nt > 1:
+        t_edges = np.linspace(tmin - 0.5 * deltat, tmax + 0.5 * deltat, nt + 1)
+        t = tmin_stf + duration * np.array([0.0, peak_ratio, 1.0])
+        f = np.array([0.0, 1.0, 0.0])
+        amplitudes = plf_integrate_piecewise(t_edges, t, f)
+        amplitudes /= np.sum(amplitudes)
+    else:
+        amplitudes = np.ones(1)
+    times = np.linspace(tmin, tmax, nt)
+    return times, amplitudes
+
+
+def stf_discretize_t(gprob, src, deltat):
+    """The source time function BEAT attaches to a geometry-mode source: ``stf_catalog[stf_type](anchor=-1)``
+    (beat/config.py:2058-2060; catalogue beat/sources.py:723-729 = pyrocko's Boxcar / Triangular / HalfSinusoid); the
+    sampled ``duration`` (and ``peak_ratio`` for the triangle) reach it through utility.update_source (:773-797)."""
+    kind = gprob.get("stf_type", "HalfSinusoid")
+    anchor = gprob["stf_anchor"]
+    if kind == "HalfSinusoid":
+        return halfsinusoid_discretize_t(src["duration"], anchor, deltat, src["time"])
+    if kind == "Boxcar":
+        return boxcar_discretize_t(src["duration"], anchor, deltat, src["time"])
+    if kind == "Triangular":
+        return triangular_discretize_t(src["duration"], src.get("peak_ratio", gprob.get("peak_ratio", 0.5)), anchor, deltat, src["time"])
+    raise ValueError("unknown stf_type %r" % (kind,))
+
+
 # --------------------------------------------------------------------------------------
 # geometry: source -> receiver distance, azimuth, back-azimuth
 # --------------------------------------------------------------------------------------
@@ -297,7 +413,7 @@ def seismogram(gprob, wm, t, src):
     dist, azi, bazi = source_receiver_geometry(gprob["event"]["lat"], gprob["event"]["lon"], src["north_shift"],
                                                src["east_shift"], wm["lats"][t], wm["lons"][t])
     m6 = dc_m6(src["strike"], src["dip"], src["rake"], magnitude_to_moment(src["magnitude"]))
-    times, amps = halfsinusoid_discretize_t(src["duration"], gprob["stf_anchor"], store["deltat"], src["time"])
+    times, amps = stf_discretize_t(gprob, src, store["deltat"])
     W = component_weights(m6, azi, bazi, wm["azimuths"][t], wm["dips"][t])
     nodes = store_nodes(store, src["depth"], dist, wm["interpolation"])
     elements = []

@@ -40,6 +40,61 @@ def test_stf_discretisation():
     assert t[0] == 8.0 and t[-1] == 12.0                                    # anchor 0: centred on the reference time
 
 
+def test_boxcar_and_triangular_stf_discretisation():
+    """The other two entries of the reference's stf_catalog (beat/sources.py:723-729): known answers of the restated
+    [pyrocko] BoxcarSTF / TriangularSTF.discretize_t."""
+    # piecewise-linear bin integrals: exact areas, jumps contribute nothing, end values continue
+    e = np.linspace(-1.0, 4.0, 11)
+    assert O.plf_integrate_piecewise(e, [0, 0, 2, 2], [0, 1, 1, 0]).sum() == pytest.approx(2.0, rel=1e-14)
+    assert O.plf_integrate_piecewise(e, [0, 1.2, 3], [0, 1, 0]).sum() == pytest.approx(1.5, rel=1e-14)
+    np.testing.assert_allclose(O.plf_integrate_piecewise([0.0, 0.5, 1.0], [0.0, 1.0], [0.0, 1.0]), [0.125, 0.375], rtol=1e-14)
+    # boxcar on the grid: 4 s from 0 s at 0.5 s sampling = half-weight end points, centroid already in place
+    t, a = O.boxcar_discretize_t(4.0, -1.0, 0.5, 0.0)
+    assert a.sum() == pytest.approx(1.0) and (t * a).sum() == pytest.approx(2.0, abs=1e-12)
+    k = np.flatnonzero(a > 1e-9)
+    np.testing.assert_allclose(a[k], np.r_[0.5, np.ones(7), 0.5] / 8.0, rtol=1e-9)
+    # off the grid: the sub-sample shift puts the discrete centroid on tref + duration / 2 (anchor -1)
+    for dur, tref in ((2.3, 0.7), (0.2, -1.13), (7.77, 3.01)):
+        t, a = O.boxcar_discretize_t(dur, -1.0, 0.5, tref)
+        assert a.sum() == pytest.approx(1.0) and np.all(a >= 0)
+        assert (t * a).sum() == pytest.approx(tref + 0.5 * dur, abs=1e-12)
+        np.testing.assert_allclose(np.diff(t), 0.5, rtol=1e-12)
+        np.testing.assert_allclose(t / 0.5, np.rint(t / 0.5), atol=1e-9)           # still on the store's time grid
+    t, a = O.boxcar_discretize_t(0.0, -1.0, 0.5, 1.3)                               # a spike between two grid points
+    np.testing.assert_allclose((t * a).sum(), 1.3, atol=1e-12)
+    assert len(t) == 2
+    # triangle: centroid ratio (1 + peak_ratio) / 3, symmetric for 0.5, onset at tref for anchor -1
+    assert O.triangular_centroid_ratio(0.5) == pytest.approx(0.5)
+    assert O.triangular_centroid_ratio(0.2) == pytest.approx(1.2 / 3.0)
+    t, a = O.triangular_discretize_t(4.0, 0.5, -1.0, 0.5, 0.0)
+    assert t[0] == 0.0 and t[-1] == 4.0 and a.sum() == pytest.approx(1.0)
+    np.testing.assert_allclose(a, a[::-1], rtol=1e-12)
+    assert a[0] == pytest.approx(0.5 * 0.25 * (0.25 / 2.0) / 2.0, rel=1e-12)        # area under the ramp up to 0.25 s / total area 2
+    t, a = O.triangular_discretize_t(4.0, 0.25, -1.0, 0.5, 0.0)
+    assert int(np.argmax(a)) == 2                                                    # apex at 1 s
+    t, a = O.triangular_discretize_t(3.0, 0.5, 0.0, 0.5, 10.0)                      # anchor 0: centroid at tref
+    assert (t * a).sum() == pytest.approx(10.0, abs=1e-12)
+    for pr in (0.0, 1.0):                                                            # degenerate apex: a saw tooth
+        t, a = O.triangular_discretize_t(2.0, pr, -1.0, 0.5, 0.3)
+        assert a.sum() == pytest.approx(1.0) and np.all(a >= 0)
+
+
+def test_stf_type_selects_the_catalogue_entry():
+    """gprob['stf_type'] routes the sampled duration / peak_ratio like config.py:2058-2060 + utility.update_source."""
+    src = dict(duration=3.0, time=0.4, peak_ratio=0.3)
+    for kind, ref in (("HalfSinusoid", O.halfsinusoid_discretize_t(3.0, -1.0, 0.5, 0.4)), ("Boxcar", O.boxcar_discretize_t(3.0, -1.0, 0.5, 0.4)),
+                      ("Triangular", O.triangular_discretize_t(3.0, 0.3, -1.0, 0.5, 0.4))):
+        t, a = O.stf_discretize_t(dict(stf_type=kind, stf_anchor=-1.0), src, 0.5)
+        np.testing.assert_array_equal(t, ref[0])
+        np.testing.assert_array_equal(a, ref[1])
+    with pytest.raises(ValueError):
+        O.stf_discretize_t(dict(stf_type="Resonator", stf_anchor=-1.0), src, 0.5)
+    gprob = S.make_geometry_problem(n_stations=2, stf_type="Triangular", seed=5)
+    assert "peak_ratio" in gprob["offsets"] and gprob["n_params"] == len(S.GEOM_VARS) + 2
+    q = S.draw_chains(gprob, 1, seed=2)[0]
+    assert O.point_to_source(gprob, S.split_point(gprob, q))["peak_ratio"] == q[gprob["offsets"]["peak_ratio"]]
+
+
 def test_geodesy_known_answers():
     lat, lon = O.ne_to_latlon(10.0, 20.0, 0.0, 0.0)
     assert (lat, lon) == pytest.approx((10.0, 20.0), abs=1e-9)

@@ -110,6 +110,61 @@ def test_stf_edge_cases():
     _assert_synth_close(got, ref)
 
 
+@pytest.mark.parametrize("stf_type,n_sources,sample_peak", [("Boxcar", 1, True), ("Triangular", 1, True), ("Triangular", 1, False),
+                                                          ("Boxcar", 2, True), ("Triangular", 2, True)])
+def test_boxcar_and_triangular_stf(stf_type, n_sources, sample_peak):
+    """The other two entries of the reference's stf_catalog (beat/sources.py:723-729; SeismicGeometryConfig.stf_type):
+    synthetics and log-likelihoods against the oracle, `peak_ratio` of the triangle sampled per chain (and per source) or fixed,
+    durations from a spike to 20 s, on and off the grid."""
+    O = _oracle()
+    gprob = S.make_geometry_problem(n_stations=2, duration_bounds=(0.0, 20.0), seed=53, stf_type=stf_type, n_sources=n_sources,
+                                    sample_peak_ratio=sample_peak)
+    if stf_type == "Triangular" and not sample_peak:
+        gprob["peak_ratio"] = 0.3
+    Q = S.draw_chains(gprob, 16, seed=8)
+    od, ot = gprob["offsets"]["duration"], gprob["offsets"]["time"]
+    Q[0, od] = 0.0
+    Q[1, od], Q[1, ot] = 0.25, 0.25
+    Q[2, od], Q[2, ot] = 4.0, 0.0                                # on the grid: whole-sample centroid shift of the boxcar
+    Q[3, od] = 20.0
+    if "peak_ratio" in gprob["offsets"]:
+        Q[4, gprob["offsets"]["peak_ratio"]], Q[5, gprob["offsets"]["peak_ratio"]] = 0.0, 1.0
+    _with_data(gprob)
+    ev = _engine(gprob)
+    got = ev.get_synthetics(Q)
+    logpts, like = ev(Q)
+    ev.close()
+    ref = np.array([O.geometry_synthetics(gprob, p) for p in _points(gprob, Q)])
+    _assert_synth_close(got, ref)
+    ref_lp = np.array([O.geometry_seismic_eval(gprob, p) for p in _points(gprob, Q)])
+    _assert_logpts_close(gprob, Q, logpts, ref_lp)
+    # the STF type matters: the half-sinusoid engine gives different synthetics for the same chains
+    base = dict(gprob, stf_type="HalfSinusoid")
+    ev = _engine(base)
+    other = ev.get_synthetics(Q)
+    ev.close()
+    assert np.abs(other[3] - got[3]).max() > 1e-3 * np.abs(got[3]).max()
+
+
+def test_stf_argument_errors():
+    from beat_b200.lib import Context
+    gprob = S.make_geometry_problem(n_stations=2, seed=54)
+    ev = _engine(gprob)
+    with pytest.raises(ValueError):
+        ev.ctx.geom_set_stf("Resonator")
+    with pytest.raises(ValueError):
+        ev.ctx.geom_set_stf("Triangular", -1.0, -1, 1.5)           # fixed peak_ratio outside [0, 1]
+    with pytest.raises(ValueError):
+        ev.ctx.geom_set_stf("Triangular", -1.0, gprob["n_params"], 0.5)   # column outside q
+    with pytest.raises(ValueError):
+        ev.ctx.geom_set_stf("Boxcar", 2.0)                        # anchor outside [-1, 1]
+    ev.close()
+    c = Context(0)
+    with pytest.raises(Exception):
+        c.geom_set_stf("Boxcar")                                 # before geom_set_source
+    c.close()
+
+
 @pytest.mark.parametrize("filterer", [
     [],
     [dict(kind="bandpass", order=4, lower_corner=0.02, upper_corner=0.5)],
