@@ -288,8 +288,9 @@ class SeisSynthesizer(_OpBase):
         B = max(p.size for p in point.values())
         batched = any(p.ndim >= 1 and p.size > 1 for p in point.values())
         Q = np.zeros((B, self._n_par))
-        if self._off_peak >= 0:
-            Q[:, self._off_peak] = 0.5 if peak is None else peak.reshape(-1)
+        off_peak = getattr(self, "_off_peak", -1)
+        if off_peak >= 0:
+            Q[:, off_peak] = 0.5 if peak is None else peak.reshape(-1)
         for i, v in enumerate(GEOM_VARS):
             Q[:, i] = point[v].reshape(-1)
         arrival = np.broadcast_to(self.arrival_times, (B, self.nt))
