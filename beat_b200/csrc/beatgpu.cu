@@ -107,7 +107,8 @@ struct beatgpu_ctx {
     std::string err;
     cudaDeviceProp prop;
     // fault
-    int nsf = 0, np_total = 0, max_np_sf = 0;
+    int nsf = 0, np_total = 0, max_np_sf = 0, max_diag = 0;
+    int sweep_pack = 1;             // BEATGPU_SWEEP_PACK=0: one chain per warp in the rupture sweep
     std::vector<int> h_nd, h_ns, h_pofs;
     std::vector<double> h_psize;
     int *d_nd = nullptr, *d_ns = nullptr, *d_pofs = nullptr;
@@ -273,10 +274,17 @@ VarRef var_ref(const beatgpu_ctx* ctx, const double* q_dev, int off, long canon)
 
 int launch_sweep(beatgpu_ctx* ctx, SweepArgs& a, int n_items)
 {
-    size_t per_warp = (size_t)4 * a.max_np_sf * sizeof(double);
+    // lanes per chain: the longest grid diagonal (min(n_dip, n_strike) cells are independent per relaxation step);
+    // 32 / W chains share a warp.  BEATGPU_SWEEP_PACK=0: one chain per warp
+    int W = 32;
+    if (ctx->sweep_pack && ctx->max_diag > 0 && ctx->max_diag <= 16) W = ctx->max_diag;
+    const int cpw = 32 / W;
+    a.group_width = W;
+    const int n_warps = (n_items + cpw - 1) / cpw;
+    size_t per_warp = (size_t)4 * a.max_np_sf * sizeof(double) * cpw;
     int wpb = (int)std::min<size_t>(8, std::max<size_t>(1, (48 * 1024) / per_warp));
     // latency-bound kernel: spread the warps over all SMs before stacking several on one
-    wpb = std::max(1, std::min(wpb, n_items / (2 * ctx->prop.multiProcessorCount)));
+    wpb = std::max(1, std::min(wpb, n_warps / (2 * ctx->prop.multiProcessorCount)));
     size_t smem = per_warp * wpb;
     if (smem > 48 * 1024) {
         if (smem > (size_t)ctx->prop.sharedMemPerBlockOptin)
@@ -284,6 +292,7 @@ int launch_sweep(beatgpu_ctx* ctx, SweepArgs& a, int n_items)
                         a.max_np_sf, smem, (size_t)ctx->prop.sharedMemPerBlockOptin);
         CK(cudaFuncSetAttribute(chain_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    n_items = n_warps;
     int blocks = (n_items + wpb - 1) / wpb;
     chain_sweep_kernel<<<blocks, wpb * 32, smem, ctx->stream>>>(a, wpb);
     CKL();
@@ -581,6 +590,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_CHUNK_OCC")) { int v = atoi(e); if (v >= 5 && v <= 7) c->chunk_occ = v; }
     if (const char* e = getenv("BEATGPU_L2_FRAC")) { double v = atof(e); if (v > 0.0 && v <= 4.0) c->l2_frac = v; }
     if (const char* e = getenv("BEATGPU_SPLIT_H2D")) c->split_h2d = atoi(e) != 0;
+    if (const char* e = getenv("BEATGPU_SWEEP_PACK")) c->sweep_pack = atoi(e) != 0;
     *out = c;
     return BEATGPU_OK;
 }
@@ -681,14 +691,15 @@ int beatgpu_set_fault(beatgpu_ctx* ctx, int nsf, const int32_t* nd, const int32_
     ctx->h_ns.assign(ns, ns + nsf);
     ctx->h_psize.assign(psize, psize + nsf);
     ctx->h_pofs.resize(nsf);
-    int tot = 0, mx = 0;
+    int tot = 0, mx = 0, mxd = 0;
     for (int i = 0; i < nsf; ++i) {
         if (nd[i] <= 0 || ns[i] <= 0 || !(psize[i] > 0)) return fail(ctx, BEATGPU_E_ARG, "set_fault: subfault %d has an empty grid", i);
         ctx->h_pofs[i] = tot;
         tot += nd[i] * ns[i];
         mx = std::max(mx, nd[i] * ns[i]);
+        mxd = std::max(mxd, std::min(nd[i], ns[i]));
     }
-    ctx->nsf = nsf; ctx->np_total = tot; ctx->max_np_sf = mx;
+    ctx->nsf = nsf; ctx->np_total = tot; ctx->max_np_sf = mx; ctx->max_diag = mxd;
     int rc;
     if ((rc = upload_vec(ctx, &ctx->d_nd, ctx->h_nd.data(), nsf))) return rc;
     if ((rc = upload_vec(ctx, &ctx->d_ns, ctx->h_ns.data(), nsf))) return rc;
