@@ -109,6 +109,7 @@ struct beatgpu_ctx {
     // fault
     int nsf = 0, np_total = 0, max_np_sf = 0, max_diag = 0;
     int sweep_pack = 1;             // BEATGPU_SWEEP_PACK=0: one chain per warp in the rupture sweep
+    int misfit_warp = 1;            // BEATGPU_MISFIT_WARP=0: CTA-per-(chain, target) misfit pass for every trace length
     std::vector<int> h_nd, h_ns, h_pofs;
     std::vector<double> h_psize;
     int *d_nd = nullptr, *d_ns = nullptr, *d_pofs = nullptr;
@@ -276,8 +277,10 @@ int launch_sweep(beatgpu_ctx* ctx, SweepArgs& a, int n_items)
 {
     // lanes per chain: the longest grid diagonal (min(n_dip, n_strike) cells are independent per relaxation step);
     // 32 / W chains share a warp.  BEATGPU_SWEEP_PACK=0: one chain per warp
+    // Packing trades latency (a warp runs until the slowest of its chains has converged: 121 vs 100 us for 500 chains)
+    // for issue slots (137 vs 172 us for 4000 chains): pack once the unpacked grid would put >= 12 warps on every SM.
     int W = 32;
-    if (ctx->sweep_pack && ctx->max_diag > 0 && ctx->max_diag <= 16) W = ctx->max_diag;
+    if (ctx->sweep_pack && ctx->max_diag > 0 && ctx->max_diag <= 16 && n_items >= 12 * ctx->prop.multiProcessorCount) W = ctx->max_diag;
     const int cpw = 32 / W;
     a.group_width = W;
     const int n_warps = (n_items + cpw - 1) / cpw;
@@ -417,6 +420,25 @@ void derive_chunk(const beatgpu_ctx* ctx, const WaveMap& w, int nvar, int np, in
 }
 
 // chunked path: partial synthetics per (chain, target, patch chunk), then residual + misfit
+// residual + misfit + logpt of every (chain, target): warp-per-item kernel for short traces with diagonal / banded
+// weights (BEATGPU_MISFIT_WARP=0 disables it), CTA-per-item kernel otherwise
+int launch_misfit(beatgpu_ctx* ctx, const MisfitArgs& m)
+{
+    const long n_items = (long)m.nt * m.B;
+    if (ctx->misfit_warp && m.misfit_mode != MISFIT_DENSE && m.ns <= kMisfitWarpMaxNs) {
+        const unsigned grid = (unsigned)((n_items + kStackWarps - 1) / kStackWarps);
+        if (m.ns <= 128) misfit_warp_kernel<4><<<grid, kStackThreads, 0, ctx->stream>>>(m);
+        else misfit_warp_kernel<8><<<grid, kStackThreads, 0, ctx->stream>>>(m);
+        CKL();
+        return BEATGPU_OK;
+    }
+    const size_t smem = (size_t)m.ns * sizeof(double);
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    misfit_kernel<<<(unsigned)n_items, kStackThreads, smem, ctx->stream>>>(m);
+    CKL();
+    return BEATGPU_OK;
+}
+
 int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
 {
     ChunkArgs ca;
@@ -476,11 +498,7 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
     m.misfit_mode = a.misfit_mode; m.bw = a.bw; m.dense_upper = a.dense_upper;
     m.W = a.W; m.slog_pdet = a.slog_pdet; m.nsamp = a.nsamp;
     m.logpts = a.logpts; m.logpts_sc = a.logpts_sc; m.out_ofs = a.out_ofs;
-    const size_t smem = (size_t)a.ns * sizeof(double);
-    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    misfit_kernel<<<(unsigned)((long)a.nt * a.B), kStackThreads, smem, ctx->stream>>>(m);
-    CKL();
-    return BEATGPU_OK;
+    return launch_misfit(ctx, m);
 }
 
 void fill_static(const WaveMap& w, StackArgs& a, int nvar)
@@ -591,6 +609,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_L2_FRAC")) { double v = atof(e); if (v > 0.0 && v <= 4.0) c->l2_frac = v; }
     if (const char* e = getenv("BEATGPU_SPLIT_H2D")) c->split_h2d = atoi(e) != 0;
     if (const char* e = getenv("BEATGPU_SWEEP_PACK")) c->sweep_pack = atoi(e) != 0;
+    if (const char* e = getenv("BEATGPU_MISFIT_WARP")) c->misfit_warp = atoi(e) != 0;
     *out = c;
     return BEATGPU_OK;
 }
@@ -1202,10 +1221,7 @@ static int misfit_batch_core(beatgpu_ctx* ctx, WaveMap& w, int B, const double* 
         a.misfit_mode = w.misfit_mode; a.bw = w.bw; a.dense_upper = w.dense_upper;
         a.W = w.d_W; a.slog_pdet = w.d_slog_pdet; a.nsamp = w.d_nsamp;
         a.logpts = d_logpts; a.logpts_sc = logpts_sc; a.out_ofs = out_ofs; a.chain_bad = chain_bad;
-        const size_t smem = (size_t)w.ns * sizeof(double);
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(misfit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        misfit_kernel<<<(unsigned)((long)w.nt * B), kStackThreads, smem, ctx->stream>>>(a);
-        CKL();
+        if ((rc = launch_misfit(ctx, a))) return rc;
     }
     return BEATGPU_OK;
 }

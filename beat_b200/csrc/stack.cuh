@@ -394,6 +394,74 @@ __global__ void __launch_bounds__(kStackThreads) misfit_kernel(MisfitArgs a)
     }
 }
 
+// Short traces (ns <= 32 * NI) with diagonal or banded weights: one WARP per (chain, target), four items per CTA, no
+// block-level barrier.  A lane owns samples lane, lane + 32, ...; the loads of all its samples of up to four chunk
+// partials are in flight together (the pass is a pure HBM stream of the partials: 1.7 GB at C3 / 4000 chains).  Same
+// per-sample arithmetic as misfit_kernel (partials summed in chunk order, banded dot product in j order); only the
+// order in which the squared terms are added differs (deterministic).
+constexpr int kMisfitWarpMaxNs = 256;
+
+template <int NI>
+__global__ void __launch_bounds__(kStackThreads) misfit_warp_kernel(MisfitArgs a)
+{
+    __shared__ double rs[kStackWarps][32 * NI + 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long item = (long)blockIdx.x * kStackWarps + warp;
+    if (item >= (long)a.B * a.nt) return;
+    const int c = (int)(item % a.B), t = (int)(item / a.B);
+    const int ns = a.ns;
+    double* r = rs[warp];
+    double s[NI];
+    if (a.partial) {
+        const double* pp = a.partial + ((long)c * a.nt + t) * a.nchunk * ns;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { const int k = lane + 32 * i; s[i] = (k < ns) ? __ldcs(pp + k) : 0.0; }
+#pragma unroll 4
+        for (int j = 1; j < a.nchunk; ++j) {
+            double v[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) { const int k = lane + 32 * i; v[i] = (k < ns) ? __ldcs(pp + (long)j * ns + k) : 0.0; }
+#pragma unroll
+            for (int i = 0; i < NI; ++i) s[i] += v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { const int k = lane + 32 * i; if (k < ns) r[k] = a.data[(long)t * ns + k] - s[i]; }   // seismic.py:1332
+    } else {
+        const double* rr = a.resid + ((long)c * a.nt + t) * ns;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { const int k = lane + 32 * i; if (k < ns) r[k] = __ldg(rr + k); }
+    }
+    __syncwarp();
+    double q = 0.0;
+    if (a.misfit_mode == MISFIT_DIAG) {
+        const double* Wt = a.W + (long)t * ns;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) { const int k = lane + 32 * i; if (k < ns) { const double z = Wt[k] * r[k]; q = fma(z, z, q); } }
+    } else {
+        const double* Wt = a.W + (long)t * (a.bw + 1) * ns;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int k = lane + 32 * i;
+            if (k < ns) {
+                double z = 0.0;
+                const int jmax = min(a.bw, ns - 1 - k);
+                for (int j = 0; j <= jmax; ++j) z = fma(Wt[(long)j * ns + k], r[k + j], z);
+                q = fma(z, z, q);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) {
+        const double hp = a.hyp[(long)c * a.hyp_sc + a.hyper_idx[t]];
+        const double M = (double)(short)a.nsamp[t];
+        const double norm = M * (2.0 * hp + 1.8378770664093453);
+        double lp = (-0.5) * (a.slog_pdet[t] + norm + (1.0 / exp(hp * 2.0)) * q);
+        if (a.chain_bad && a.chain_bad[c]) lp = CUDART_NAN;
+        a.logpts[(long)c * a.logpts_sc + a.out_ofs + t] = lp;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Patch-chunked stacking: one WARP per (target, patch-chunk, chain) item, items ordered (t, chunk, c) so that all
 // warps resident at a time gather from the same few (t, p) library blocks (chunk * nvar * ndur*nst*ld*sizeof(T)

@@ -425,6 +425,31 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
+def bind_to_gpu_numa(torch, device):
+    """N > 1: pin this rank to the CPU cores NVML names as local to its GPU BEFORE the pinned host buffers are allocated,
+    so that they are first touched on the GPU's NUMA node (eight ranks copying q from one node share its memory
+    controller and the inter-socket link).  Returns a short description for the JSON line; never fatal."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device).uuid)
+        uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus or len(cpus) == len(os.sched_getaffinity(0)):
+            return "not bound (NVML affinity = the whole process mask)"
+        os.sched_setaffinity(0, cpus)
+        return "bound to %d GPU-local cores (NVML)" % len(cpus)
+    except Exception as e:
+        return "not bound (%s)" % type(e).__name__
+
+
 def run_gpu_arm(args):
     # stdout carries exactly ONE line (the JSON): native libraries (NCCL prints its version banner with printf) write
     # to file descriptor 1 directly, so fd 1 points at stderr until the line is ready
@@ -502,6 +527,7 @@ def _run_gpu_arm(args):
         os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=device)
 
+    host_affinity = bind_to_gpu_numa(torch, device) if n_gpus > 1 else "single rank: not bound"
     a = c3_args(args.quick)
     # c4 / c5 are named with a GLOBAL population (BASELINE.json: n_chains = 2000 on 4 GPUs; PT with 512 chains on 8 GPUs),
     # partitioned over the ranks like the reference partitions n_chains over its workers (sampler/smc.py:423-427)
@@ -723,7 +749,7 @@ def _run_gpu_arm(args):
             "dtype": DTYPE_LABEL[args.store], "data": "synthetic", "config": workload_config(args, n_gpus, B),
             "e2e": {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": B * prob["n_params"] * 8,
                     "d2h_bytes_per_step": B * (ev.n_out + 1) * 8, "ms_per_step": head["e2e_ms_per_step"],
-                    "vs_resident": head["e2e_value"] / head["value"]},
+                    "vs_resident": head["e2e_value"] / head["value"], "host_affinity": host_affinity},
             "gpu_launches": head["launches"],
             "sampler_step": {"value": sampler_value, "unit": "chain-steps/s", "mode": sampler_mode, "eager_value": sampler_eager,
                              "what": "lock-step Metropolis step (proposal + bounds + batched eval + accept) with the population resident on the device",

@@ -39,9 +39,14 @@ def test_sweep_golden_reference_c(golden):
         c.close()
 
 
-@pytest.mark.parametrize("nd,ns,h", [(10, 20, 2.0), (10, 15, 2.5), (1, 7, 1.0), (9, 1, 3.0), (24, 40, 1.0), (40, 33, 0.5)])
-def test_sweep_bitexact_vs_port(nd, ns, h):
-    """Anti-diagonal wavefront schedule == sequential Gauss-Seidel, bit for bit, incl. the iteration count."""
+@pytest.mark.parametrize("pack", ["1", "0"])
+@pytest.mark.parametrize("nd,ns,h", [(10, 20, 2.0), (10, 15, 2.5), (1, 7, 1.0), (9, 1, 3.0), (24, 40, 1.0), (40, 33, 0.5), (16, 16, 1.0),
+                                     (5, 30, 2.0), (3, 3, 4.0)])
+def test_sweep_bitexact_vs_port(nd, ns, h, pack, monkeypatch):
+    """Anti-diagonal wavefront schedule == sequential Gauss-Seidel, bit for bit, incl. the iteration count -- with one
+    chain per warp and with several chains sharing a warp (lane groups of min(nd, ns) lanes: 3 chains on a 10-row fault,
+    2 on 16 x 16, 6 on 5 x 30, 10 on 3 x 3, 32 on a single row; chains of a warp converge after different iteration counts)."""
+    monkeypatch.setenv("BEATGPU_SWEEP_PACK", pack)
     from beat_b200.lib import Context
     rng = np.random.default_rng(nd * 100 + ns)
     B = 3000
@@ -55,6 +60,23 @@ def test_sweep_bitexact_vs_port(nd, ns, h):
     assert np.array_equal(got, ref)
     assert np.array_equal(it, it_ref)
     c.close()
+
+
+def test_sweep_packed_subfaults_of_different_shape():
+    """Fused path, two subfaults with different grids, enough chains for the packed sweep: the lane groups of one warp
+    then relax grids of different shape (different diagonal counts); start times bit-identical to the sequential C."""
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=2, subfaults=((4, 7, 2.0), (6, 5, 1.5)), ns=16, ndur=3, seed=77)
+    B = 1200                                         # 2400 (chain, subfault) items >= 12 per SM: packed
+    Q = synthetic.draw_chains(prob, B, seed=9)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    logpts, _ = ev(Q)
+    st = ev.starttimes(B)
+    ev.close()
+    for b in list(range(0, B, 97)) + [B - 1]:
+        lp, _, t0 = O.ffi_seismic_eval(prob, synthetic.split_point(prob, Q[b]), impl="port", return_synth=True)
+        assert np.array_equal(st[b], t0), b
+        np.testing.assert_allclose(logpts[b], lp, rtol=1e-10)
 
 
 def test_sweeper_op_reference_test_case():
@@ -186,7 +208,9 @@ CASES = {
     "three_slipvars": dict(slip_vars=("uparr", "uperp", "utens")),
     "one_slipvar": dict(slip_vars=("uparr",)),
     "two_wavemaps": dict(n_wavemaps=2),
-    "long_traces": dict(ns=300, nt=3),
+    "long_traces": dict(ns=300, nt=3),                  # > 256 samples: CTA-per-item misfit pass
+    "mid_traces": dict(ns=200, nt=3),                   # 129..256 samples: warp-per-item misfit pass, 8 samples per lane
+    "mid_traces_variance": dict(ns=161, nt=3, noise="variance"),
     "many_patches": dict(subfaults=((12, 25, 1.0),), nt=2, ns=16),
     "odd_ns": dict(ns=37),
 }
@@ -359,8 +383,9 @@ def test_near_map_accuracy_f32_storage():
     {"BEATGPU_STACK_MODE": "fused", "BEATGPU_PERSISTENT": "1"},
     {"BEATGPU_STACK_MODE": "chunked", "BEATGPU_CHUNK": "7"},
     {"BEATGPU_STACK_MODE": "chunked", "BEATGPU_CHUNK": "32"},
+    {"BEATGPU_STACK_MODE": "chunked", "BEATGPU_CHUNK": "7", "BEATGPU_MISFIT_WARP": "0"},      # CTA-per-item misfit pass for short traces too
 ])
-@pytest.mark.parametrize("case", ["ml_exp", "nn_exp", "station_corr_hp_specific", "two_subfaults", "long_traces", "odd_ns", "ml_dense"])
+@pytest.mark.parametrize("case", ["ml_exp", "nn_exp", "station_corr_hp_specific", "two_subfaults", "long_traces", "mid_traces", "odd_ns", "ml_dense"])
 def test_stack_execution_modes_vs_oracle(env, case, monkeypatch):
     """Every scheduling variant of the stacking kernel (one CTA per item, persistent CTAs, patch-chunked warps with a
     separate misfit pass) must give the oracle's answer; violations surface as IndexError in all of them."""
