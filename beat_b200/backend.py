@@ -30,11 +30,18 @@ class BatchedNumpyChains(object):
     """Append the per-step outputs of all chains to ``<dir_path>/chain-<i>.bin`` in NumpyChain layout.
 
     var_shapes: OrderedDict name -> shape tuple (order = ``model.unobserved_RVs`` order, beat/sampler/metropolis.py:160-162);
-    var_dtypes: name -> numpy dtype string (default float64)."""
+    var_dtypes: name -> numpy dtype string (default float64).
+
+    ``n_io_threads = 0``: ``flush`` writes the files before it returns (the reference's behaviour).  ``n_io_threads > 0``:
+    two step buffers; a full buffer is handed to a pool of writer threads (chains split between them; the strided gather of
+    a chain's records and the file append both release the GIL) while the sampler fills the other one -- the sampler only
+    waits when the writers are a whole buffer behind.  ``pinned=True`` page-locks the buffers (torch) so that a GPU sampler
+    can copy a step's packed records straight into ``slot()`` (see ``DeviceRecorder``) without any host-side packing."""
 
     flat_names_tag, var_shape_tag, var_dtypes_tag = "flat_names", "var_shapes", "var_dtypes"   # backend.py:680-682
 
-    def __init__(self, dir_path, var_shapes, n_chains, var_dtypes=None, buffer_size=5000, chain_offset=0):
+    def __init__(self, dir_path, var_shapes, n_chains, var_dtypes=None, buffer_size=5000, chain_offset=0, n_io_threads=0,
+                 pinned=False):
         os.makedirs(dir_path, exist_ok=True)
         self.dir_path = dir_path
         self.var_shapes = OrderedDict((k, tuple(v)) for k, v in var_shapes.items())
@@ -45,9 +52,38 @@ class BatchedNumpyChains(object):
         self.data_structure = np.dtype({"names": self.varnames,
                                         "formats": ["{}{}".format(self.var_shapes[n], self.var_dtypes[n]) for n in self.varnames]})
         self.buffer_size = buffer_size
-        self._buf = np.zeros((buffer_size, n_chains), dtype=self.data_structure)
+        self.n_io_threads = int(n_io_threads)
+        self._pinned_keep = []
+        n_buf = 2 if self.n_io_threads > 0 else 1
+        self._bufs = [self._alloc(pinned) for _ in range(n_buf)]
+        self._pending = [[] for _ in range(n_buf)]              # futures of the flush that last used each buffer
+        self._cur = 0
+        self._buf = self._bufs[0]
         self._n = 0
         self.stored_samples = 0
+        # one single-worker executor per writer thread and a FIXED chain -> thread map: a chain's appends of successive
+        # flushes then run in submission order (one shared pool would let a later flush overtake an earlier one)
+        self._pool = None
+        if self.n_io_threads > 0:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = [ThreadPoolExecutor(max_workers=1, thread_name_prefix="beat_b200_trace%d" % i) for i in range(self.n_io_threads)]
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self, pinned):
+        shape = (self.buffer_size, self.n_chains)
+        if not pinned:
+            return np.zeros(shape, dtype=self.data_structure)
+        import torch
+        t = torch.zeros(self.buffer_size * self.n_chains * self.data_structure.itemsize, dtype=torch.uint8).pin_memory()
+        self._pinned_keep.append(t)
+        return t.numpy().view(self.data_structure).reshape(shape)
+
+    @property
+    def record_width(self):
+        """float64 values per record when every variable is float64 (the packed-record fast path), else None."""
+        if any(np.dtype(d) != np.float64 for d in self.var_dtypes.values()):
+            return None
+        return self.data_structure.itemsize // 8
 
     def filename(self, chain):
         return os.path.join(self.dir_path, "chain-{}.bin".format(chain + self.chain_offset))
@@ -61,25 +97,116 @@ class BatchedNumpyChains(object):
                 with open(self.filename(c), "wb") as fh:
                     fh.write(header)
 
+    # ------------------------------------------------------------------ filling
     def write(self, values):
         """Buffer one step of all chains.  values: dict name -> array [n_chains, *shape]."""
         if self._n == self.buffer_size:
-            self.flush()
+            self.flush(wait=False)
         row = self._buf[self._n]
         for name in self.varnames:
             row[name] = np.asarray(values[name]).reshape((self.n_chains,) + self.var_shapes[name])
         self._n += 1
 
-    def flush(self):
-        """Append every chain's buffered records to its file (backend.py:822-845) and clear the buffer."""
-        if self._n == 0:
-            return
-        block = self._buf[: self._n]
-        for c in range(self.n_chains):
+    def slot(self):
+        """The next step's records as a float64 matrix [n_chains, record_width] INSIDE the buffer (all-float64 layouts):
+        fill it (e.g. by a device-to-host copy), then call ``commit()``."""
+        if self.record_width is None:
+            raise TypeError("packed records need an all-float64 layout")
+        if self._n == self.buffer_size:
+            self.flush(wait=False)
+        return self._buf[self._n].view(np.float64).reshape(self.n_chains, self.record_width)
+
+    def commit(self):
+        self._n += 1
+
+    def write_records(self, rec):
+        """One step of all chains already packed in record order: rec [n_chains, record_width] float64."""
+        self.slot()[...] = rec
+        self.commit()
+
+    # ------------------------------------------------------------------ writing
+    def _append_chains(self, block, c0, c1):
+        for c in range(c0, c1):
             with open(self.filename(c), mode="ab") as fh:
-                np.ascontiguousarray(block[:, c]).tofile(fh)
-        self.stored_samples += self._n
-        self._n = 0
+                np.ascontiguousarray(block[:, c]).tofile(fh)         # backend.py:822-845: records appended with tofile
+
+    def flush(self, wait=True):
+        """Append every chain's buffered records to its file (backend.py:822-845) and clear the buffer.  With writer
+        threads and ``wait=False`` the append runs in the background and filling continues in the other buffer."""
+        if self._n > 0:
+            block = self._buf[: self._n]
+            if self._pool is None:
+                self._append_chains(block, 0, self.n_chains)
+            else:
+                per = -(-self.n_chains // self.n_io_threads)
+                self._pending[self._cur] = [self._pool[i].submit(self._append_chains, block, i * per, min(self.n_chains, (i + 1) * per))
+                                            for i in range(self.n_io_threads) if i * per < self.n_chains]
+                self._cur = (self._cur + 1) % len(self._bufs)
+                self._wait(self._cur)                                   # the buffer we are about to fill must be on disk
+                self._buf = self._bufs[self._cur]
+            self.stored_samples += self._n
+            self._n = 0
+        if wait:
+            for i in range(len(self._bufs)):
+                self._wait(i)
+
+    def _wait(self, i):
+        for f in self._pending[i]:
+            f.result()                                                  # re-raises a writer thread's exception here
+        self._pending[i] = []
+
+    def close(self):
+        try:
+            self.flush(wait=True)
+        finally:
+            if self._pool is not None:
+                for ex in self._pool:
+                    ex.shutdown(wait=True)
+                self._pool = None
+
+
+class DeviceRecorder(object):
+    """``on_step`` companion for a GPU sampler: packs a step's outputs in record order ON THE DEVICE (one ``torch.cat``),
+    copies the packed matrix into the writer's page-locked buffer on a side stream, and lets the writer's threads put it on
+    disk -- the sampling stream never waits for the host.  ``record(*tensors)``: tensors in the writer's variable order,
+    each [n_chains, k] or [n_chains].  ``finish()`` drains the copies and flushes."""
+
+    def __init__(self, writer, torch, device):
+        if writer.record_width is None:
+            raise TypeError("DeviceRecorder needs an all-float64 record layout")
+        self.w, self.torch, self.device = writer, torch, device
+        self.stream = torch.cuda.Stream(device=device)
+        self._last = None                                  # event of the newest copy
+        self._keep = []                                    # packed device matrices whose copies may still be in flight
+
+    def record(self, *tensors):
+        torch, w = self.torch, self.w
+        rec = torch.cat([t.reshape(w.n_chains, -1) for t in tensors], dim=1)
+        if rec.shape[1] != w.record_width or rec.dtype != torch.float64:
+            raise ValueError("packed record is %s %s, the layout wants [%d, %d] float64" % (tuple(rec.shape), rec.dtype, w.n_chains, w.record_width))
+        if w._n == w.buffer_size:                          # the buffer is about to be flushed: its copies must have landed
+            self._drain()
+        dst = torch.from_numpy(w.slot())                   # view into the writer's page-locked buffer
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ready)
+            dst.copy_(rec, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._last = done
+        self._keep.append(rec)
+        w.commit()
+
+    def _drain(self):
+        if self._last is not None:
+            self._last.synchronize()
+            self._last = None
+        self._keep = []
+
+    def finish(self):
+        self._drain()
+        self.w.flush(wait=True)
 
 
 def read_chain(filename):

@@ -255,6 +255,10 @@ def cpu_baseline(args, n_evals_per_core=4, cores=None):
             "sample": "%d chains of the same C3 shapes (f64 host library, %s), one chain per call: "
                       "%s fast_sweep + numpy stack_all (%s) + numpy mvn-chol llk, fork pool over %d cores"
                       % (n, prob["host_library"], "reference's compiled" if have_ref else "C-restated", args.interpolation, cores)}
+    _CPU.clear()                         # drops the shared host library (26.7 GB at C3) before the GPU arm starts
+    del prob
+    import gc
+    gc.collect()
     return info, allc
 
 
@@ -845,27 +849,57 @@ def pt_driver_leg(args, ev, prob, lower, upper, n_chains, n_gpus, rank, device, 
 
 def sampler_with_trace_writer(args, prob, mh, qs, lps, lks, B, n_gpus, rank, barrier, max_over_ranks):
     """The lock-step Metropolis step with every chain's record of every step written in the reference's binary trace
-    format (beat/backend.py:651-897; beat_b200.backend.BatchedNumpyChains): D2H of the step's outputs into a pinned
-    buffer, structured-array packing, one append per chain and flush.  A few steps only: 4000 chain files per rank."""
+    format (beat/backend.py:651-897; beat_b200.backend.BatchedNumpyChains): the step's outputs are packed in record
+    order on the device, copied into the writer's page-locked step buffers on a side stream (DeviceRecorder) and appended
+    to the chain files by writer threads while the sampler goes on (`value`); for comparison the synchronous path of
+    round 1 -- D2H, host-side packing, appends before the next step (`synchronous`).  4000 chain files per rank."""
     import shutil
     import tempfile
     from collections import OrderedDict
     import torch
-    from beat_b200.backend import BatchedNumpyChains
+    from beat_b200.backend import BatchedNumpyChains, DeviceRecorder
     shapes = OrderedDict()
     for name, n in prob["var_order"]:
         shapes[name] = (int(n),)
     shapes["seis_like"] = (int(lps.shape[1]),)
     shapes["like"] = ()
-    steps = max(2, min(args.steps, 5))
+    off = prob["offsets"]
+    device = qs.device
+    out = {}
     d = tempfile.mkdtemp(prefix="beat_b200_trace_r%d_" % rank)
     try:
-        w = BatchedNumpyChains(d, shapes, B, buffer_size=steps)
+        # ---- asynchronous: device-packed records, page-locked double buffers, writer threads
+        steps, n_thr = max(8, args.steps), 4
+        w = BatchedNumpyChains(os.path.join(d, "async"), shapes, B, buffer_size=4, n_io_threads=n_thr, pinned=True)
+        w.setup()
+        rec = DeviceRecorder(w, torch, device)
+        for _ in range(2):
+            qs, lps, lks, _ = mh.step(qs, lps, lks)
+            rec.record(qs, lps, lks)
+        rec.finish()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            qs, lps, lks, _ = mh.step(qs, lps, lks)
+            rec.record(qs, lps, lks)
+        rec.finish()                                                  # every record of every chain is in its file
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        w.close()
+        nbytes = steps * B * w.data_structure.itemsize
+        out = {"value": n_gpus * B * steps / dt, "unit": "chain-steps/s", "steps": steps, "writer_threads": n_thr,
+               "bytes_written_per_rank": int(nbytes), "write_MBps_per_rank": nbytes / dt / 1e6,
+               "what": "same step + records packed on the device, D2H into page-locked step buffers on a side stream, one NumpyChain-format "
+                       "record per chain per step appended to %d chain files per rank by %d writer threads (wall clock incl. the final flush)" % (B, n_thr)}
+        shutil.rmtree(os.path.join(d, "async"), ignore_errors=True)
+
+        # ---- synchronous (round-1 path)
+        steps = max(2, min(args.steps, 4))
+        w = BatchedNumpyChains(os.path.join(d, "sync"), shapes, B, buffer_size=steps)
         w.setup()
         host_q = torch.empty(qs.shape, dtype=torch.float64).pin_memory()
         host_lp = torch.empty(lps.shape, dtype=torch.float64).pin_memory()
         host_lk = torch.empty(lks.shape, dtype=torch.float64).pin_memory()
-        off = prob["offsets"]
 
         def record(q, lp, lk):
             host_q.copy_(q, non_blocking=True); host_lp.copy_(lp, non_blocking=True); host_lk.copy_(lk, non_blocking=True)
@@ -875,9 +909,6 @@ def sampler_with_trace_writer(args, prob, mh, qs, lps, lks, B, n_gpus, rank, bar
             vals["seis_like"], vals["like"] = host_lp.numpy(), host_lk.numpy()
             w.write(vals)
 
-        qs, lps, lks, _ = mh.step(qs, lps, lks)
-        record(qs, lps, lks)
-        w.flush()
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -886,10 +917,9 @@ def sampler_with_trace_writer(args, prob, mh, qs, lps, lks, B, n_gpus, rank, bar
         w.flush()
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)
-        nbytes = steps * B * w.data_structure.itemsize
-        return {"value": n_gpus * B * steps / dt, "unit": "chain-steps/s", "steps": steps,
-                "bytes_written_per_rank": int(nbytes), "write_MBps_per_rank": nbytes / dt / 1e6,
-                "what": "same step + D2H of q/logpts/like + one NumpyChain-format record per chain per step appended to %d chain files per rank (wall clock)" % B}
+        out["synchronous"] = {"value": n_gpus * B * steps / dt, "steps": steps,
+                              "what": "D2H, host-side packing and the appends inside the step (round-1 path)"}
+        return out
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

@@ -47,6 +47,50 @@ def test_batched_chains_byte_compatible(tmp_path):
     assert bk.create_flat_names("x", (2, 2)) == ["x__0_0", "x__0_1", "x__1_0", "x__1_1"] and bk.create_flat_names("like", ()) == ["like"]
 
 
+def test_writer_threads_and_packed_records_write_the_same_bytes(tmp_path):
+    """n_io_threads > 0 (two step buffers, background appends) and the packed-record path (`slot` / `commit`,
+    `write_records`) produce exactly the files of the synchronous dict-fed writer, whatever the buffer size."""
+    import pytest
+    rng = np.random.default_rng(4)
+    var_shapes = OrderedDict([("uparr", (6,)), ("time", (1,)), ("seis_like", (4,)), ("like", ())])
+    n_chains, n_steps = 37, 11
+    steps = [{k: rng.standard_normal((n_chains,) + s) for k, s in var_shapes.items()} for _ in range(n_steps)]
+    ref = bk.BatchedNumpyChains(str(tmp_path / "sync"), var_shapes, n_chains, buffer_size=100)
+    ref.setup()
+    for v in steps:
+        ref.write(v)
+    ref.flush()
+    assert ref.record_width == 12
+    for tag, threads, buf, packed in (("thr", 3, 4, False), ("thr1", 1, 1, False), ("packed", 2, 3, True), ("packed_sync", 0, 5, True)):
+        w = bk.BatchedNumpyChains(str(tmp_path / tag), var_shapes, n_chains, buffer_size=buf, n_io_threads=threads)
+        w.setup()
+        for i, v in enumerate(steps):
+            if packed:
+                rec = np.concatenate([np.asarray(v[k]).reshape(n_chains, -1) for k in var_shapes], axis=1)
+                if i % 2:
+                    w.write_records(rec)
+                else:
+                    w.slot()[...] = rec
+                    w.commit()
+            else:
+                w.write(v)
+        w.close()
+        assert w.stored_samples == n_steps
+        for c in range(n_chains):
+            assert open(w.filename(c), "rb").read() == open(ref.filename(c), "rb").read(), (tag, c)
+    mixed = bk.BatchedNumpyChains(str(tmp_path / "mixed"), OrderedDict([("x", (2,)), ("n", ())]), 3, var_dtypes={"n": "int32"})
+    assert mixed.record_width is None
+    with pytest.raises(TypeError):
+        mixed.slot()
+    # a writer thread's failure surfaces in the sampler's thread at the next flush / close
+    w = bk.BatchedNumpyChains(str(tmp_path / "gone"), var_shapes, n_chains, buffer_size=2, n_io_threads=2)
+    w.setup()
+    w.dir_path = str(tmp_path / "does" / "not" / "exist")
+    w.write(steps[0]); w.write(steps[1])
+    with pytest.raises(OSError):
+        w.close()
+
+
 def _golden_trace():
     import os
     return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trace_golden.npz"))

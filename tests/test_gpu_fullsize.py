@@ -108,6 +108,30 @@ def test_c3_all_chains_all_logpts_f64(c3, c3_f64, c3_oracle):
         assert np.array_equal(st[c], O.fast_sweep(1.0 / pt["velocities"], 2.0, hr, hc, 10, 20, impl="port") + pt["time"][0])
 
 
+def test_c3_all_chains_nearest_neighbor(c3, host_pool):
+    """The other interpolation mode of the reference (`nearest_neighbor`: one tap per patch, rint index mapping,
+    ffi/base.py:649-660) at full C3 size: every logpt of 512 chains, f32 library, against the oracle."""
+    import copy
+    from oracle import parallel_check as PC
+    from beat_b200.devlib import fill_library_on_device
+    from beat_b200.engine import BatchedFFILogLike
+    prob, _, _, torch, dev = c3
+    prob_nn = copy.copy(prob)
+    prob_nn["wavemaps"] = [dict(prob["wavemaps"][0], interpolation="nearest_neighbor")]
+    ev = BatchedFFILogLike.from_problem(prob_nn, device=0, store_dtype="float32", upload_libraries=False)
+    try:
+        fill_library_on_device(ev, prob_nn, torch, dev, "f32")
+        Q = synthetic.draw_chains(prob_nn, 512, seed=515)
+        ref = PC.full_size_logpts(prob_nn, Q, host_pool)
+        logpts, like = ev(Q)
+        err = np.abs(logpts / ref - 1.0)
+        _report("c3_prior_draws_f32_nearest_neighbor", chains=512, logpts=int(ref.size), max_rel_err=float(err.max()))
+        np.testing.assert_allclose(logpts, ref, rtol=1e-5)
+        np.testing.assert_allclose(like, ref.sum(axis=1), rtol=1e-5)
+    finally:
+        ev.close()
+
+
 @pytest.mark.parametrize("noise_frac", [0.05, 0.01])
 def test_c3_near_map_population(c3, c3_f64, host_pool, noise_frac):
     """Where the likelihood is most sensitive to synthetics errors: data = synth(q_true) + noise, chains in a small

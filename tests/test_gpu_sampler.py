@@ -101,6 +101,51 @@ def test_smc_ffi_with_trace_writer_on_the_gpu(tmp_path):
     ev.close()
 
 
+def test_device_recorder_streams_the_same_files_as_the_host_path(tmp_path):
+    """DeviceRecorder (records packed on the device, copied into the writer's page-locked buffers on a side stream, appended
+    by writer threads) against the synchronous dict-fed writer on the same SMC run: byte-identical chain files."""
+    from collections import OrderedDict
+    from beat_b200 import backend as bk
+    from beat_b200 import sampler as S
+    from beat_b200.engine import BatchedFFILogLike
+    prob = synthetic.make_problem(nt=4, subfaults=((3, 4, 4.0),), ns=32, ndur=4, seed=16)
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    dev = torch.device("cuda", 0)
+    lower = np.concatenate([prob["priors"][n][0] for n, _ in prob["var_order"]])
+    upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
+    n_chains, n_steps = 48, 7
+    shapes = OrderedDict((name, (int(n),)) for name, n in prob["var_order"])
+    shapes["seis_like"] = (ev.n_out,)
+    shapes["like"] = ()
+    off = prob["offsets"]
+    host_w, dev_w, recs = {}, {}, {}
+
+    def on_step(stage, step, q, logpts, like):
+        if stage not in host_w:
+            host_w[stage] = bk.BatchedNumpyChains(str(tmp_path / ("host_%d" % stage)), shapes, n_chains, buffer_size=100)
+            dev_w[stage] = bk.BatchedNumpyChains(str(tmp_path / ("dev_%d" % stage)), shapes, n_chains, buffer_size=3, n_io_threads=2, pinned=True)
+            host_w[stage].setup(); dev_w[stage].setup()
+            recs[stage] = bk.DeviceRecorder(dev_w[stage], torch, dev)
+        recs[stage].record(q, logpts, like)                       # q's columns are in var_order: the record is q | logpts | like
+        qn = q.cpu().numpy()
+        vals = {name: qn[:, off[name]:off[name] + n] for name, n in prob["var_order"]}
+        vals["seis_like"], vals["like"] = logpts.cpu().numpy(), like.cpu().numpy()
+        host_w[stage].write(vals)
+
+    out = S.smc_sample(ev.eval_device, lower, upper, n_chains=n_chains, n_steps=n_steps, device=dev, seed=5, max_stages=3, on_step=on_step)
+    assert out["n_stages"] >= 2
+    for st in host_w:
+        host_w[st].flush()
+        recs[st].finish()
+        dev_w[st].close()
+        assert dev_w[st].stored_samples == host_w[st].stored_samples == n_steps
+        for c in range(n_chains):
+            assert open(dev_w[st].filename(c), "rb").read() == open(host_w[st].filename(c), "rb").read(), (st, c)
+    with pytest.raises(ValueError):
+        recs[max(recs)].record(torch.zeros((n_chains, 3), dtype=torch.float64, device=dev))
+    ev.close()
+
+
 def test_metropolis_step_as_one_cuda_graph():
     """cuda_graph=True: proposal, bounds check, the batched evaluation (libbeatgpu's kernels captured on torch's stream),
     accept / reject and the in-place state update replay as ONE CUDA graph.  The run is deterministic, its bookkeeping
