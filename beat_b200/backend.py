@@ -32,10 +32,12 @@ class BatchedNumpyChains(object):
     var_shapes: OrderedDict name -> shape tuple (order = ``model.unobserved_RVs`` order, beat/sampler/metropolis.py:160-162);
     var_dtypes: name -> numpy dtype string (default float64).
 
-    ``n_io_threads = 0``: ``flush`` writes the files before it returns (the reference's behaviour).  ``n_io_threads > 0``:
-    two step buffers; a full buffer is handed to a pool of writer threads (chains split between them; the strided gather of
-    a chain's records and the file append both release the GIL) while the sampler fills the other one -- the sampler only
-    waits when the writers are a whole buffer behind.  ``pinned=True`` page-locks the buffers (torch) so that a GPU sampler
+    ``n_io_threads = 0``: ``flush`` writes the files before it returns, chain by chain with ``ndarray.tofile`` (the
+    reference's behaviour, pure numpy).  ``n_io_threads > 0``: two step buffers; a full buffer is handed to ONE background
+    thread that calls the native ``beatgpu_trace_append`` (libbeatgpu: every chain's records leave with one ``writev``
+    straight from the step-major buffer, chains split over ``n_io_threads`` native threads, no interpreter lock) while the
+    sampler fills the other buffer -- the sampler only waits when the writers are a whole buffer behind.  Flushes are
+    queued on that one thread, so a chain's appends keep their order.  ``pinned=True`` page-locks the buffers (torch) so that a GPU sampler
     can copy a step's packed records straight into ``slot()`` (see ``DeviceRecorder``) without any host-side packing."""
 
     flat_names_tag, var_shape_tag, var_dtypes_tag = "flat_names", "var_shapes", "var_dtypes"   # backend.py:680-682
@@ -61,12 +63,13 @@ class BatchedNumpyChains(object):
         self._buf = self._bufs[0]
         self._n = 0
         self.stored_samples = 0
-        # one single-worker executor per writer thread and a FIXED chain -> thread map: a chain's appends of successive
-        # flushes then run in submission order (one shared pool would let a later flush overtake an earlier one)
         self._pool = None
         if self.n_io_threads > 0:
             from concurrent.futures import ThreadPoolExecutor
-            self._pool = [ThreadPoolExecutor(max_workers=1, thread_name_prefix="beat_b200_trace%d" % i) for i in range(self.n_io_threads)]
+            from . import lib as _beatlib
+            _beatlib.load()                                  # fail here, not in the background thread, if the library is missing
+            self._native_append = _beatlib.trace_append
+            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="beat_b200_trace")   # one thread: flushes stay ordered
 
     # ------------------------------------------------------------------ buffers
     def _alloc(self, pinned):
@@ -138,9 +141,8 @@ class BatchedNumpyChains(object):
             if self._pool is None:
                 self._append_chains(block, 0, self.n_chains)
             else:
-                per = -(-self.n_chains // self.n_io_threads)
-                self._pending[self._cur] = [self._pool[i].submit(self._append_chains, block, i * per, min(self.n_chains, (i + 1) * per))
-                                            for i in range(self.n_io_threads) if i * per < self.n_chains]
+                self._pending[self._cur] = [self._pool.submit(self._native_append, self.dir_path, self.chain_offset, block,
+                                                              self.n_io_threads)]
                 self._cur = (self._cur + 1) % len(self._bufs)
                 self._wait(self._cur)                                   # the buffer we are about to fill must be on disk
                 self._buf = self._bufs[self._cur]
@@ -160,8 +162,7 @@ class BatchedNumpyChains(object):
             self.flush(wait=True)
         finally:
             if self._pool is not None:
-                for ex in self._pool:
-                    ex.shutdown(wait=True)
+                self._pool.shutdown(wait=True)
                 self._pool = None
 
 

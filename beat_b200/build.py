@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "beatgpu.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("beatgpu.cu", "sweep.cuh", "stack.cuh", "aux.cuh", "gemm.cuh", "tma.cuh", "probe.cuh", "geom.cuh", "geom_host.inc")] + [
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("beatgpu.cu", "sweep.cuh", "stack.cuh", "aux.cuh", "gemm.cuh", "tma.cuh", "probe.cuh", "geom.cuh", "geom_host.inc", "trace_io.inc")] + [
     os.path.join(ROOT, "include", "beatgpu.h")]
 OUT = os.path.join(HERE, "libbeatgpu.so")
 

@@ -1705,3 +1705,4 @@ int beatgpu_probe_gather(beatgpu_ctx* ctx, int mode, int64_t ws_bytes, int row_b
 }  // extern "C"
 
 #include "geom_host.inc"
+#include "trace_io.inc"

@@ -20,7 +20,7 @@ NEAREST, MULTILINEAR = 0, 1
 INTERPOLATION = {"nearest_neighbor": NEAREST, "multilinear": MULTILINEAR}
 MAX_SLIPVARS = 3
 
-E_CUDA, E_ARG, E_INDEX, E_NOTREADY, E_NONFINITE = 1, 2, 3, 4, 5
+E_CUDA, E_ARG, E_INDEX, E_NOTREADY, E_NONFINITE, E_IO = 1, 2, 3, 4, 5, 6
 
 
 class BeatGpuLibraryError(ImportError):
@@ -117,6 +117,7 @@ _SIGNATURES = {
     "beatgpu_geom_loglike_batch": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_geom_loglike_batch_dev": (C.c_int, [_P, C.c_int, _P, _P, _P]),
     "beatgpu_geom_synthetics_batch": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
+    "beatgpu_trace_append": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int64, _P, C.c_int]),
     "beatgpu_probe_gather": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_double)]),
 }
@@ -174,6 +175,24 @@ def _check_q(q, n_params, what):
     if q.ndim != 2 or (n_params is not None and q.shape[1] != n_params):
         raise ValueError("%s: q must be [B, %s], got %s" % (what, n_params, q.shape))
     return q
+
+
+def trace_append(dir_path, chain_offset, records, n_threads=4):
+    """Append the step-major record block ``records`` ([n_steps, n_chains] structured, or [n_steps, n_chains, k]) to the
+    chain files of ``dir_path`` (native writev + threads, beatgpu_trace_append; no CUDA context needed).  Raises OSError."""
+    lib = load()
+    records = np.ascontiguousarray(records)
+    n_steps, n_chains = records.shape[0], records.shape[1]
+    rec_bytes = records.dtype.itemsize * int(np.prod(records.shape[2:], dtype=np.int64))
+    rc = lib.beatgpu_trace_append(os.fsencode(dir_path), int(chain_offset), int(n_chains), int(n_steps), int(rec_bytes),
+                                  records.ctypes.data_as(C.c_void_p), int(n_threads))
+    if rc:
+        msg = lib.beatgpu_last_error(None).decode()
+        if rc == E_IO:
+            raise OSError(msg)
+        if rc == E_ARG:
+            raise ValueError(msg)
+        raise BeatGpuError(rc, msg)
 
 
 class Context:

@@ -47,21 +47,21 @@ def main():
     on_step = None
     if args.trace_dir and world == 1:
         from collections import OrderedDict
-        from beat_b200.backend import BatchedNumpyChains
+        from beat_b200.backend import BatchedNumpyChains, DeviceRecorder
         shapes_out = OrderedDict([(n, (s,)) for n, s in prob["var_order"]] + [("seis_like", (ev.n_out,)), ("like", ())])
-        writers = {}
+        writers, recorders = {}, {}
 
         def on_step(stage, step, q, logpts, like):
-            w = writers.get(stage)
-            if w is None:
-                for old in writers.values():
-                    old.flush()
-                w = writers[stage] = BatchedNumpyChains(os.path.join(args.trace_dir, "stage_%d" % stage), shapes_out, q.shape[0], buffer_size=args.steps)
+            # records packed on the device (q's columns are in var_order: record = q | seis_like | like), copied into
+            # page-locked step buffers on a side stream, appended to the chain files by writer threads
+            if stage not in writers:
+                for st in writers:
+                    recorders[st].finish()
+                w = writers[stage] = BatchedNumpyChains(os.path.join(args.trace_dir, "stage_%d" % stage), shapes_out, q.shape[0],
+                                                        buffer_size=min(16, args.steps), n_io_threads=4, pinned=True)
                 w.setup()
-            qh = q.cpu().numpy()
-            vals = {n: qh[:, prob["offsets"][n]: prob["offsets"][n] + s] for n, s in prob["var_order"]}
-            vals["seis_like"], vals["like"] = logpts.cpu().numpy(), like.cpu().numpy()
-            w.write(vals)
+                recorders[stage] = DeviceRecorder(w, torch, q.device)
+            recorders[stage].record(q, logpts, like)
 
     t0 = time.perf_counter()
     out = sampler.smc_sample(ev.eval_device, lower, upper, n_chains=args.chains, n_steps=args.steps, device=dev, seed=1,
@@ -69,8 +69,9 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     if on_step:
-        for w in writers.values():
-            w.flush()
+        for st, w in writers.items():
+            recorders[st].finish()
+            w.close()
     if rank == 0:
         print("stages %d, %d forward+loglike evaluations in %.1f s = %.0f evals/s on %d GPU(s); median llk %.2f"
               % (out["n_stages"], out["n_evals"], dt, out["n_evals"] / dt, world, np.median(out["likelihoods"])))

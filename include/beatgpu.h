@@ -41,6 +41,7 @@ extern "C" {
 #define BEATGPU_E_INDEX       3      /* a GF-library index left the library (IndexError)      */
 #define BEATGPU_E_NOTREADY    4      /* an operand required by the call has not been uploaded */
 #define BEATGPU_E_NONFINITE   5      /* reserved: non-finite llk (ValueError in the sampler)  */
+#define BEATGPU_E_IO          6      /* file I/O of the trace writer failed (OSError)         */
 
 /* storage dtype of a GF library on the device */
 #define BEATGPU_F32 0
@@ -336,6 +337,17 @@ int beatgpu_geom_synthetics_batch(beatgpu_ctx* ctx, int wmap_id, int B, const do
  * entries report theirs as BEATGPU_E_CUDA).  The chains concerned already carry NaN logpts (rejected by a sampler);
  * a non-zero count means the device lost copies.  Reads and resets the counter; synchronises.                  */
 int beatgpu_geom_timeouts(beatgpu_ctx* ctx, int64_t* count);
+
+/* ---------------------------------------------------------------- trace files (host only) ----
+ * Append n_steps records of each of n_chains chains to <dir_path>/chain-<chain_offset + c>.bin -- what
+ * NumpyChain.record_buffer does per chain with ndarray.tofile on a file opened in append mode
+ * (beat/backend.py:822-845; file layout :765-820).  records: [n_steps, n_chains, rec_bytes], step-major (what a lock-step
+ * sampler produces: the outputs of all chains per step); every chain's records are written with one writev straight
+ * from that buffer, chains split over n_threads native threads.  The files must exist with their header
+ * (BatchedNumpyChains.setup).  No CUDA context involved; errors: BEATGPU_E_IO, message via beatgpu_last_error(NULL)
+ * on the calling thread.                                                                                       */
+int beatgpu_trace_append(const char* dir_path, int chain_offset, int n_chains, int n_steps, int64_t rec_bytes,
+                         const void* records, int n_threads);
 
 /* Diagnostics (not on the product path): measured ceiling of the access pattern the GF stacking uses.  Gathers
  * pseudo-random rows of row_bytes (multiple of 16, <= 16384) from a zero-filled working set of ws_bytes with

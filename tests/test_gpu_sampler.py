@@ -105,6 +105,7 @@ def test_device_recorder_streams_the_same_files_as_the_host_path(tmp_path):
     """DeviceRecorder (records packed on the device, copied into the writer's page-locked buffers on a side stream, appended
     by writer threads) against the synchronous dict-fed writer on the same SMC run: byte-identical chain files."""
     from collections import OrderedDict
+    import torch
     from beat_b200 import backend as bk
     from beat_b200 import sampler as S
     from beat_b200.engine import BatchedFFILogLike
