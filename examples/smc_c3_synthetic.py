@@ -45,7 +45,7 @@ def main():
     upper = np.concatenate([prob["priors"][n][1] for n, _ in prob["var_order"]])
 
     on_step = None
-    if args.trace_dir and world == 1:
+    if args.trace_dir:                                   # every rank writes the files of its own chains
         from collections import OrderedDict
         from beat_b200.backend import BatchedNumpyChains, DeviceRecorder
         shapes_out = OrderedDict([(n, (s,)) for n, s in prob["var_order"]] + [("seis_like", (ev.n_out,)), ("like", ())])
@@ -58,7 +58,8 @@ def main():
                 for st in writers:
                     recorders[st].finish()
                 w = writers[stage] = BatchedNumpyChains(os.path.join(args.trace_dir, "stage_%d" % stage), shapes_out, q.shape[0],
-                                                        buffer_size=min(16, args.steps), n_io_threads=4, pinned=True)
+                                                        buffer_size=min(16, args.steps), chain_offset=rank * q.shape[0],
+                                                        n_io_threads=4, pinned=True)
                 w.setup()
                 recorders[stage] = DeviceRecorder(w, torch, q.device)
             recorders[stage].record(q, logpts, like)

@@ -48,7 +48,7 @@ def main():
     out["dram_bytes_per_launch"] = out["dram_bytes_read"] + out["dram_bytes_write"]
     out["l2_to_sm_bytes"] = out["lts_sectors_read"] * 32
     if len(sys.argv) > 3:
-        mis = [r for r in raw_rows(sys.argv[3]) if r["Kernel Name"][1].startswith("misfit_kernel")]
+        mis = [r for r in raw_rows(sys.argv[3]) if "misfit" in r["Kernel Name"][1] and "gf_stack" not in r["Kernel Name"][1]]
         if mis:
             out["misfit_kernel_dram_bytes"] = val(mis[0], "dram__bytes_read.sum") + val(mis[0], "dram__bytes_write.sum")
             out["dram_bytes_per_launch"] += out["misfit_kernel_dram_bytes"]
