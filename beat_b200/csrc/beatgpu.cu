@@ -150,7 +150,7 @@ struct beatgpu_ctx {
     // ring of event pairs: one per fused evaluation, so the kernels' share of a timed loop can be summed afterwards
     std::vector<cudaEvent_t> tev;                  // 2 * kTimingRing events, created on first use
     int tev_next = 0, tev_pending = 0;             // next slot; evaluations recorded since the last reset (<= kTimingRing)
-    double l2_frac = 0.4;                          // BEATGPU_L2_FRAC: share of L2 one patch chunk of the library may span
+    double l2_frac = 0.6;                          // BEATGPU_L2_FRAC: share of L2 one patch chunk of the library may span (nominal bytes; chains touch part of a block)
     bool chunk_forced = false;                     // BEATGPU_CHUNK given: no L2-derived chunk
     cudaStream_t copy_stream = nullptr;            // second stream of the host-pointer entry (q columns behind the sweep)
     cudaEvent_t copy_done = nullptr, copy_go = nullptr;

@@ -242,7 +242,7 @@ int beatgpu_stack_ms_accum(beatgpu_ctx* ctx, int reset, double* sum_ms, int64_t*
 
 /* How the stacking pass of a wavemap is blocked for the L2 cache: patches per chunk, number of chunks, the library
  * bytes one chunk spans (chunk * n_slipvars * ndurations * nstarttimes * row bytes) and the device's L2 size.  The
- * chunk is derived from cudaDeviceProp.l2CacheSize (working set <= 40 % of L2; BEATGPU_L2_FRAC / BEATGPU_CHUNK
+ * chunk is derived from cudaDeviceProp.l2CacheSize (working set <= 60 % of L2, nominal bytes; BEATGPU_L2_FRAC / BEATGPU_CHUNK
  * override) so that libraries with larger per-patch blocks keep the all-chains-stream-through-L2 behaviour.   */
 int beatgpu_stack_blocking(beatgpu_ctx* ctx, int wmap_id, int n_slipvars, int* chunk_patches, int* n_chunks,
                            int64_t* chunk_bytes, int64_t* l2_bytes);
