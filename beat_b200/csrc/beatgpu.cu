@@ -401,7 +401,7 @@ int timing_end(beatgpu_ctx* ctx)
 // Patches per chunk of the chunked stacking pass.  All chains stream through one (target, chunk) slice of the library
 // while it is L2 resident, so the slice -- chunk * nvar * ndur * nst * ld * sizeof(T) bytes -- must stay well below the
 // L2 size: 40 % of cudaDeviceProp.l2CacheSize (the partial-synthetic stores and the other operands share the cache),
-// at most kChunkMax (one lane plans one patch), and not so small that the partials scratch explodes (<= 24 chunks).
+// at most kChunkMax (a lane plans up to two patches), and not so small that the partials scratch explodes (<= 24 chunks).
 void derive_chunk(const beatgpu_ctx* ctx, const WaveMap& w, int nvar, int np, int* chunk, int* nchunk, int64_t* chunk_bytes)
 {
     const int64_t esz = (w.store_dtype == BEATGPU_F32) ? 4 : 8;

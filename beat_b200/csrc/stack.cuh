@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(kStackThreads) misfit_warp_kernel(MisfitArgs a
 // barrier at all (plan, stream, store are warp-private).  Partial synthetics go to a [B, nt, nchunk, ns] f64
 // scratch; misfit_kernel sums them in chunk order and finishes residual + misfit.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kChunkMax = 32;            // patches per chunk (one lane plans one patch)
+constexpr int kChunkMax = 64;            // patches per chunk (a lane plans patches lane, lane + 32)
 constexpr int kChunkWarps = 4;
 
 struct ChunkArgs {
@@ -509,12 +509,13 @@ gf_stack_chunk_kernel(ChunkArgs ca)
     if (a.corr) corr = a.corr[(long)c * a.corr_sc + a.station_idx[t]];
     // ---- plan (one lane per patch; same arithmetic as the fused kernel / ffi/base.py:506-517,553-564,676-679)
     bool viol = false;
-    if (lane < pn) {
-        const int p = p0 + lane;
+    for (int i = lane; i < pn; i += 32) {
+        const int p = p0 + i;
         Plan pl;
-        viol = make_patch_plan<T, K, NVAR>(a, c, t, p, dur[p], st[p], corr, pl);
-        if (viol) atomicAdd(a.violations, 1ULL);
-        plan[lane] = pl;
+        const bool v = make_patch_plan<T, K, NVAR>(a, c, t, p, dur[p], st[p], corr, pl);
+        if (v) atomicAdd(a.violations, 1ULL);
+        viol = viol || v;
+        plan[i] = pl;
     }
     const bool any_viol = __any_sync(0xffffffffu, viol);
     __syncwarp();

@@ -42,11 +42,11 @@ def test_parity_for_every_chunking(monkeypatch, shape, l2_frac):
         np.testing.assert_allclose(logpts, ref, rtol=rtol)
         np.testing.assert_allclose(like, ref.sum(axis=1), rtol=rtol)
         npatch = prob["npatches"]
-        assert blk["n_chunks"] == -(-npatch // blk["chunk_patches"]) and 1 <= blk["chunk_patches"] <= 32
+        assert blk["n_chunks"] == -(-npatch // blk["chunk_patches"]) and 1 <= blk["chunk_patches"] <= 64
         frac = float(l2_frac) if l2_frac else 0.6
         per_patch = blk["chunk_bytes"] // blk["chunk_patches"]
         # the chunk honours the L2 budget unless the floor (<= 24 chunks, bounded scratch) or one patch alone exceeds it
-        floor = min(32, -(-npatch // 24))
+        floor = min(64, -(-npatch // 24))
         assert blk["chunk_bytes"] <= max(frac * blk["l2_bytes"], floor * per_patch, per_patch) + per_patch
         assert blk["l2_bytes"] > 32 << 20
         seen[store] = blk
