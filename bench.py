@@ -829,7 +829,7 @@ def pt_driver_leg(args, ev, prob, lower, upper, n_chains, n_gpus, rank, device, 
     import torch
     from beat_b200 import sampler as S
     from beat_b200 import synthetic
-    n_samples = max(60, 12 * args.steps)
+    n_samples = max(200, 50 * args.steps)                      # long enough to amortise the per-call graph capture and warm-up
     pop = synthetic.draw_chains(prob, n_chains, seed=97)                  # identical on every rank
     kw = dict(device=device, swap_interval=(10, 15), n_chains_posterior=max(1, n_chains // 8), t_scale=1.2,
               beta_tune_interval=4 * n_chains, proposal_cov=np.diag(((upper - lower) * 0.005) ** 2), tune_interval=20,
