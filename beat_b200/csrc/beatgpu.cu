@@ -145,6 +145,9 @@ struct beatgpu_ctx {
     int geo_mode = 1;               // 1 = FP64 tensor-core GEMM tiles (BEATGPU_GEO_MODE=mma), 0 = one CTA per (chain, dataset)
     double* d_partial = nullptr;    // [B, nt, nchunk, ns] scratch of the chunked path
     size_t partial_bytes = 0;
+    void* d_plan = nullptr;         // per-(chain, patch) plans of the chunked path (plan_cache_kernel)
+    size_t plan_bytes = 0;
+    int plan_cache_on = 1;          // BEATGPU_PLAN_CACHE=0: every (target, chunk, chain) warp plans its own patches
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;      // event pair of the LAST evaluation (aliases into the ring below)
     bool ev_valid = false;
     // ring of event pairs: one per fused evaluation, so the kernels' share of a timed loop can be summed afterwards
@@ -365,6 +368,37 @@ int launch_chunk_nvar(beatgpu_ctx* ctx, const ChunkArgs& ca)
     return BEATGPU_OK;
 }
 
+// plan of every (chain, patch) once per evaluation (see plan_cache_kernel): valid when start times do not depend on the target
+template <typename T, int K>
+int launch_plan_cache(beatgpu_ctx* ctx, ChunkArgs& ca)
+{
+    const StackArgs& a = ca.s;
+    const long n = (long)a.B * a.np;
+    size_t esz = 0;
+    switch (a.nvar) {
+        case 1: esz = sizeof(PatchPlan<T, K, 1>); break;
+        case 2: esz = sizeof(PatchPlan<T, K, 2>); break;
+        case 3: esz = sizeof(PatchPlan<T, K, 3>); break;
+        default: return fail(ctx, BEATGPU_E_ARG, "n_slipvars must be 1..3, got %d", a.nvar);
+    }
+    const size_t need = (size_t)n * esz;
+    if (ctx->plan_bytes < need) {
+        if (ctx->d_plan) cudaFree(ctx->d_plan);
+        ctx->d_plan = nullptr; ctx->plan_bytes = 0;
+        CK(cudaMalloc(&ctx->d_plan, need));
+        ctx->plan_bytes = need;
+    }
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    switch (a.nvar) {
+        case 1: plan_cache_kernel<T, K, 1><<<grid, 128, 0, ctx->stream>>>(ca, (PatchPlan<T, K, 1>*)ctx->d_plan); break;
+        case 2: plan_cache_kernel<T, K, 2><<<grid, 128, 0, ctx->stream>>>(ca, (PatchPlan<T, K, 2>*)ctx->d_plan); break;
+        default: plan_cache_kernel<T, K, 3><<<grid, 128, 0, ctx->stream>>>(ca, (PatchPlan<T, K, 3>*)ctx->d_plan); break;
+    }
+    CKL();
+    ca.plan_cache = ctx->d_plan;
+    return BEATGPU_OK;
+}
+
 constexpr int kTimingRing = 1024;
 
 bool stream_capturing(beatgpu_ctx* ctx)
@@ -459,6 +493,14 @@ int launch_stack_chunked(beatgpu_ctx* ctx, const WaveMap& w, const StackArgs& a)
         const int mt = (a.ns + kGemmBM - 1) / kGemmBM;
         if ((rc = ensure_tmp(ctx, 4, (size_t)a.nt * a.B * a.ns * sizeof(double)))) return rc;
         if ((rc = ensure_tmp(ctx, 5, (size_t)a.nt * a.B * mt * sizeof(double)))) return rc;
+    }
+    ca.plan_cache = nullptr;
+    if (ctx->plan_cache_on && a.st_st == 0 && a.corr == nullptr && a.nt > 1) {     // start times independent of the target
+        if (w.store_dtype == BEATGPU_F32)
+            rc = (w.interp == BEATGPU_NEAREST) ? launch_plan_cache<float, 1>(ctx, ca) : launch_plan_cache<float, 4>(ctx, ca);
+        else
+            rc = (w.interp == BEATGPU_NEAREST) ? launch_plan_cache<double, 1>(ctx, ca) : launch_plan_cache<double, 4>(ctx, ca);
+        if (rc) return rc;
     }
     if (w.store_dtype == BEATGPU_F32)
         rc = (w.interp == BEATGPU_NEAREST) ? launch_chunk_nvar<float, 1>(ctx, ca) : launch_chunk_nvar<float, 4>(ctx, ca);
@@ -610,6 +652,7 @@ int beatgpu_ctx_create(int device, beatgpu_ctx** out)
     if (const char* e = getenv("BEATGPU_SPLIT_H2D")) c->split_h2d = atoi(e) != 0;
     if (const char* e = getenv("BEATGPU_SWEEP_PACK")) c->sweep_pack = atoi(e) != 0;
     if (const char* e = getenv("BEATGPU_MISFIT_WARP")) c->misfit_warp = atoi(e) != 0;
+    if (const char* e = getenv("BEATGPU_PLAN_CACHE")) c->plan_cache_on = atoi(e) != 0;
     *out = c;
     return BEATGPU_OK;
 }
@@ -632,7 +675,7 @@ void beatgpu_ctx_destroy(beatgpu_ctx* ctx)
     cudaFree(ctx->d_nd); cudaFree(ctx->d_ns); cudaFree(ctx->d_pofs); cudaFree(ctx->d_psize); cudaFree(ctx->d_fixed);
     cudaFree(ctx->d_q); cudaFree(ctx->d_logpts); cudaFree(ctx->d_like); cudaFree(ctx->d_t0); cudaFree(ctx->d_bad);
     cudaFree(ctx->d_viol);
-    cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_partial); cudaFree(ctx->d_plan);
     for (int i = 0; i < 6; ++i) cudaFree(ctx->d_tmp[i]);
     for (auto& st : ctx->gstores) { cudaFree(st.d_traces); cudaFree(st.d_itmin); cudaFree(st.d_nsamp); }
     for (auto& g : ctx->gwmaps) {

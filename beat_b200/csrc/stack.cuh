@@ -479,7 +479,31 @@ struct ChunkArgs {
     int nchunk;
     uint32_t zero_mask;                   // always 0; opaque to the compiler (load-scheduling dependence, see the kernel)
     double* partial;                      // [B, nt, nchunk, ns]
+    const void* plan_cache;               // optional PatchPlan<T,K,NVAR> [B, np] of target 0 (plan_cache_kernel), or nullptr
 };
+
+// Without station corrections the plan of a (chain, patch) -- library indices and weights -- is the same for every target
+// (start times do not depend on the target, seismic.py:1283-1296; only the target's block offset differs), yet every
+// (target, chunk, chain) warp would recompute it: 64 times at C3.  This kernel computes it once per (chain, patch) for
+// target 0; the chunk kernel then loads its patches' plans (one coalesced read) and adds the target offset.  A violating
+// tap is counted once per target (as the per-target plans would) and its weights become NaN so that the partial sums and
+// the logpt of that chain do.
+template <typename T, int K, int NVAR>
+__global__ void __launch_bounds__(128) plan_cache_kernel(ChunkArgs ca, PatchPlan<T, K, NVAR>* __restrict__ cache)
+{
+    const StackArgs& a = ca.s;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)a.B * a.np) return;
+    const int c = (int)(idx / a.np), p = (int)(idx % a.np);
+    PatchPlan<T, K, NVAR> pl;
+    const bool viol = make_patch_plan<T, K, NVAR>(a, c, 0, p, a.dur[(long)c * a.dur_sc + p], a.st[(long)c * a.st_sc + p], 0.0, pl);
+    if (viol) {
+        atomicAdd(a.violations, (unsigned long long)a.nt);
+#pragma unroll
+        for (int q = 0; q < K * NVAR; ++q) pl.w[q] = (T)CUDART_NAN;
+    }
+    cache[idx] = pl;
+}
 
 // MINB: CTAs per SM the register allocation must allow (__launch_bounds__): 5 leaves the multilinear kernels their natural
 // ~96 registers (16 row loads of two patches in flight per lane), 6 / 7 cap them at 80 / 72 (more resident warps, fewer
@@ -509,13 +533,24 @@ gf_stack_chunk_kernel(ChunkArgs ca)
     if (a.corr) corr = a.corr[(long)c * a.corr_sc + a.station_idx[t]];
     // ---- plan (one lane per patch; same arithmetic as the fused kernel / ffi/base.py:506-517,553-564,676-679)
     bool viol = false;
-    for (int i = lane; i < pn; i += 32) {
-        const int p = p0 + i;
-        Plan pl;
-        const bool v = make_patch_plan<T, K, NVAR>(a, c, t, p, dur[p], st[p], corr, pl);
-        if (v) atomicAdd(a.violations, 1ULL);
-        viol = viol || v;
-        plan[i] = pl;
+    if (ca.plan_cache) {
+        const Plan* pc = reinterpret_cast<const Plan*>(ca.plan_cache) + (long)c * a.np + p0;
+        const uint32_t toff = (uint32_t)((long)t * a.np * a.ndur * a.nst) * (uint32_t)(a.ld * (long)sizeof(T) / 16);   // target block, 16-byte units
+        for (int i = lane; i < pn; i += 32) {
+            Plan pl = pc[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pl.off[k] += toff;
+            plan[i] = pl;
+        }
+    } else {
+        for (int i = lane; i < pn; i += 32) {
+            const int p = p0 + i;
+            Plan pl;
+            const bool v = make_patch_plan<T, K, NVAR>(a, c, t, p, dur[p], st[p], corr, pl);
+            if (v) atomicAdd(a.violations, 1ULL);
+            viol = viol || v;
+            plan[i] = pl;
+        }
     }
     const bool any_viol = __any_sync(0xffffffffu, viol);
     __syncwarp();
