@@ -181,3 +181,57 @@ def test_pt_sharded_over_two_ranks(tmp_path):
     assert x.shape[0] > 10000
     np.testing.assert_allclose(np.abs(x).mean(axis=0), 0.5, rtol=0.0, atol=0.05)
     assert 0.02 < (x[:, 0] > 0).mean() < 0.35
+
+
+def _trace_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from collections import OrderedDict
+    from beat_b200 import backend as bk
+    from beat_b200 import distributed as D
+    from beat_b200 import sampler as S
+    D.init_process_group(backend="gloo")
+    n, n_chains, n_steps = 3, 40, 9
+    mu = torch.tensor([0.3, -0.2, 0.1], dtype=torch.float64)
+
+    def ev(q):
+        lp = -0.5 * ((q - mu) ** 2 / 0.05).sum(dim=1, keepdim=True)
+        return lp, lp[:, 0]
+
+    shapes = OrderedDict([("x", (n,)), ("seis_like", (1,)), ("like", ())])
+    writers = {}
+
+    def on_step(stage, step, q, logpts, like):
+        # every rank writes the files of ITS chains: chain_offset = first global chain of the shard; native appends
+        if stage not in writers:
+            n_local = q.shape[0]
+            writers[stage] = bk.BatchedNumpyChains(os.path.join(out_dir, "stage_%d" % stage), shapes, n_local, buffer_size=4,
+                                                   chain_offset=rank * n_local, n_io_threads=2)
+            writers[stage].setup()
+        writers[stage].write_records(torch.cat([q, logpts, like[:, None]], dim=1).numpy())
+
+    res = S.smc_sample(ev, -np.ones(n), np.ones(n), n_chains, n_steps, seed=3, on_step=on_step)
+    for w in writers.values():
+        w.close()
+    np.savez(os.path.join(out_dir, "trace_r%d.npz" % rank), pop=res["population"], like=res["likelihoods"], n_stages=res["n_stages"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_trace_files_written_by_two_ranks(tmp_path):
+    """Two ranks stream the steps of their chain shards into one stage directory (disjoint chain numbers through
+    ``chain_offset``, background native appends): afterwards every chain of the population has its file with n_steps
+    records whose last one is that chain's end point."""
+    from beat_b200 import backend as bk
+    port = _free_port()
+    mp.spawn(_trace_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(os.path.join(str(tmp_path), "trace_r0.npz"))
+    n_stages, pop, like = int(r0["n_stages"]), r0["pop"], r0["like"]
+    assert n_stages >= 2 and pop.shape == (40, 3)
+    last = os.path.join(str(tmp_path), "stage_%d" % n_stages)
+    assert sorted(os.listdir(last)) == sorted("chain-%d.bin" % c for c in range(40))
+    for c in range(40):
+        x = bk.get_values(os.path.join(last, "chain-%d.bin" % c), "x")
+        assert x.shape == (9, 3)
+        np.testing.assert_array_equal(x[-1], pop[c])
+        np.testing.assert_array_equal(bk.get_values(os.path.join(last, "chain-%d.bin" % c), "like")[-1], like[c])
