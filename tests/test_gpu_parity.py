@@ -637,3 +637,25 @@ def test_cuda_loglike_matches_reference_get_formula_golden(name, hp_specific):
     ev.close()
     np.testing.assert_allclose(logpts, g[tag + "_logpts"], rtol=1e-8)
     np.testing.assert_allclose(like, g[tag + "_logpts"].sum(axis=1), rtol=1e-8)
+
+
+@pytest.mark.parametrize("geo_mode", ["mma", "simple"])
+@pytest.mark.parametrize("name", ["one_dataset", "three_datasets", "two_datasets_one_slipvar"])
+def test_cuda_geodetic_loglike_matches_reference_get_formula_golden(name, geo_mode, monkeypatch):
+    """The geodetic columns of the fused CUDA evaluation (DMMA GEMM path and the matvec path) against per-dataset logpts
+    produced by the reference's own GeodeticDistributerComposite.get_formula, run eagerly (committed fixture
+    tests/golden/geodetic_composite_golden.npz, tests/golden/make_geodetic_composite_golden.py); no oracle in the loop.
+    The six chains of the fixture are tiled to 36 so that the batched GEMM path (B >= 32) is the one that runs."""
+    from test_oracle_golden import GEODETIC_COMPOSITE_CASES, load_geodetic_composite_golden
+    from beat_b200.engine import BatchedFFILogLike
+    monkeypatch.setenv("BEATGPU_GEO_MODE", geo_mode)
+    g = load_geodetic_composite_golden()
+    prob = synthetic.make_problem(**GEODETIC_COMPOSITE_CASES[name])
+    Q, ref = np.tile(g[name + "_Q"], (6, 1)), np.tile(g[name + "_logpts"], (6, 1))
+    ev = BatchedFFILogLike.from_problem(prob, store_dtype="float64")
+    logpts, like = ev(Q)
+    ev.close()
+    nt, nd = prob["wavemaps"][0]["nt"], ref.shape[1]
+    assert logpts.shape == (36, nt + nd)
+    np.testing.assert_allclose(logpts[:, nt:nt + nd], ref, rtol=1e-10)
+    np.testing.assert_allclose(like, logpts.sum(axis=1), rtol=1e-10, atol=1e-10 * np.abs(logpts).sum(axis=1).max())

@@ -220,3 +220,30 @@ def test_oracle_matches_reference_get_formula(name, hp_specific):
     for q, ref in zip(g[tag + "_Q"], g[tag + "_logpts"]):
         mine = O.ffi_seismic_eval(prob, synthetic.split_point(prob, q), impl="auto")
         np.testing.assert_allclose(mine, ref, rtol=1e-10)
+
+
+GEODETIC_COMPOSITE_CASES = {
+    "one_dataset": dict(nt=2, subfaults=((4, 6, 2.0),), ns=16, ndur=3, seed=401, geodetic=dict(nobs=[40])),
+    "three_datasets": dict(nt=2, subfaults=((3, 5, 2.5),), ns=16, ndur=3, seed=402, geodetic=dict(nobs=[30, 17, 5])),
+    "two_datasets_one_slipvar": dict(nt=2, subfaults=((3, 4, 2.0),), ns=16, ndur=3, seed=403, geodetic=dict(nobs=[12, 21]),
+                                     slip_vars=("uparr",)),
+}
+
+
+def load_geodetic_composite_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "geodetic_composite_golden.npz"))
+
+
+@pytest.mark.parametrize("name", sorted(GEODETIC_COMPOSITE_CASES))
+def test_oracle_matches_reference_geodetic_get_formula(name):
+    """Golden per-dataset logpts ("geo_like") from the reference's OWN GeodeticDistributerComposite.get_formula
+    (beat/models/geodetic.py:1030-1084), executed eagerly through the numpy-backed pytensor shim: GeodeticGFLibrary.stack_all
+    per slip component, (sdata - mu) * sodws, Bij.srmap, multivariate_normal_chol
+    (tests/golden/make_geodetic_composite_golden.py).  Pins rows a6 / a7 / a8 of the oracle at composite level."""
+    from beat_b200 import synthetic
+    g = load_geodetic_composite_golden()
+    prob = synthetic.make_problem(**GEODETIC_COMPOSITE_CASES[name])
+    for q, ref in zip(g[name + "_Q"], g[name + "_logpts"]):
+        mine = O.ffi_geodetic_eval(prob["geodetic"], synthetic.split_point(prob, q))
+        np.testing.assert_allclose(mine, ref, rtol=1e-10)
