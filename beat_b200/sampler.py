@@ -47,6 +47,27 @@ def tune_scale(scale, acc_rate):
     return s
 
 
+def tune_pt_scale(scale, acc_rate):
+    """Temperature-scale adaptation of the PT ladder (beat/sampler/pt.py:37-73 ``tune``; applied by
+    ``TemperingManager.tune_betas``, :331-352, and clipped there to [1.01, 2.0]): gentler than the Metropolis step rule.
+
+    Rate    scale
+    <0.001  x 0.85 ; <0.05  x 0.9 ; <0.2  x 0.95 ; >0.5  x 1.05 ; >0.75  x 1.10 ; >0.95  x 1.15"""
+    if acc_rate < 0.001:
+        return scale * 0.85
+    if acc_rate < 0.05:
+        return scale * 0.9
+    if acc_rate < 0.2:
+        return scale * 0.95
+    if acc_rate > 0.95:
+        return scale * 1.15
+    if acc_rate > 0.75:
+        return scale * 1.10
+    if acc_rate > 0.5:
+        return scale * 1.05
+    return scale
+
+
 def calc_beta(likelihoods, beta, coef_variation=1.0):
     """Next tempering beta + importance weights by bisection (beat/sampler/smc.py:133-165), numpy on [n_chains]."""
     likelihoods = np.asarray(likelihoods, dtype=np.float64)
@@ -487,8 +508,7 @@ def pt_sample(evaluator, lower, upper, n_chains, n_samples, device=None, swap_in
         since_tune_swaps += a.size; since_tune_acc += k
         if beta_tune_interval and since_tune_swaps >= beta_tune_interval:
             rate = since_tune_acc / float(since_tune_swaps)
-            t_scale = float(np.clip(float(tune_scale(torch.tensor([t_scale], dtype=torch.float64),
-                                                      torch.tensor([rate], dtype=torch.float64))[0]), 1.01, 2.0))   # pt.py:126-127
+            t_scale = float(np.clip(tune_pt_scale(t_scale, rate), 1.01, 2.0))            # pt.py:344-348 (limits :126-127)
             ladder = pt_betas(n_chains, n_chains_posterior, t_scale)
             set_local_betas()
             scales.append(t_scale)

@@ -126,3 +126,38 @@ def test_smc_checkpoint_resume_is_bit_identical(tmp_path):
     assert resumed["n_evals"] == full["n_evals"]
     with pytest.raises(ValueError, match="checkpoint holds"):
         S.smc_sample(evaluator, lower, upper, n_chains=100, n_steps=10, seed=11, checkpoint_dir=str(tmp_path / "b"), resume=True)
+
+
+def _sampler_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampler_golden.npz"))
+
+
+def test_stage_functions_match_the_references_own():
+    """tests/golden/sampler_golden.npz: outputs of the reference's OWN SMC.calc_beta / calc_covariance / resample
+    (beat/sampler/smc.py:133-186,290-324) and pt.tune (beat/sampler/pt.py:37-73), generated by importing them from
+    /root/reference (tests/golden/make_sampler_golden.py).  Integer work (resampling indexes) is exact; the bisection is
+    the same sequence of floating-point operations, so beta and weights are bit-equal; the covariance to rounding."""
+    g = _sampler_golden()
+    for i in range(int(g["cb_n"])):
+        beta_in, cv = g["cb%d_in" % i]
+        b, old, w = S.calc_beta(g["cb%d_like" % i], float(beta_in), coef_variation=float(cv))
+        assert np.array_equal(np.array([b, old]), g["cb%d_beta" % i])
+        assert np.array_equal(w, g["cb%d_weights" % i])
+    for i in range(int(g["cov_n"])):
+        cov = S.calc_covariance(g["cov%d_pop" % i], g["cov%d_w" % i])
+        ref = g["cov%d_out" % i]
+        np.testing.assert_allclose(cov, ref, rtol=1e-12, atol=1e-14 * np.abs(ref).max())
+        assert np.all(np.linalg.eigvalsh((cov + cov.T) / 2.0) >= -1e-12 * np.abs(ref).max())
+
+    class FixedOffset:                                    # the reference draws np.random.rand(1); the fixture stores that draw
+        def __init__(self, u):
+            self.u = u
+
+        def random(self):
+            return self.u
+    for i in range(int(g["rs_n"])):
+        idx = S.resample(g["rs%d_w" % i], FixedOffset(float(g["rs%d_aux" % i])))
+        assert np.array_equal(idx, g["rs%d_idx" % i])
+    got = np.array([S.tune_pt_scale(1.3, float(a)) for a in g["pt_acc"]])
+    assert np.array_equal(got, g["pt_scale"])
