@@ -8,6 +8,7 @@ pyrocko replaced by the inert stand-ins of tests/golden/_refshim.py -- none of t
     beat.sampler.smc.SMC.calc_covariance    (smc.py:167-186)   weighted population covariance + utility.ensure_cov_psd
     beat.sampler.smc.SMC.resample           (smc.py:290-324)   Kitagawa's deterministic resampling
     beat.sampler.pt.tune                    (pt.py:37-73)      temperature-scale adaptation of the PT ladder
+    beat.sampler.pt.TemperingManager.update_betas / propose_chain_swap   (pt.py:179-214, 428-455)   ladder and swap decision
 
 run on seeded inputs; the vectors pin beat_b200.sampler.calc_beta / calc_covariance / resample / tune_pt_scale (row f1).
 
@@ -72,6 +73,29 @@ def main():
     acc = np.array([0.0, 0.0005, 0.001, 0.02, 0.05, 0.1, 0.2, 0.35, 0.5, 0.6, 0.75, 0.8, 0.95, 0.99, 1.0])
     out["pt_acc"] = acc
     out["pt_scale"] = np.array([rpt.tune(1.3, float(a)) for a in acc])
+
+    # ---- PT ladder (TemperingManager.update_betas, pt.py:179-214) and the swap decision (propose_chain_swap, :428-455)
+    for i, (n, n_post, t_scale) in enumerate(((16, 4, 1.6), (512, 64, 1.2), (5, 1, 2.0))):
+        tm = types.SimpleNamespace(n_workers_posterior=n_post, n_workers_tempered=n - n_post, current_scale=None, _betas=None,
+                                   _worker_package_mapping={})
+        rpt.TemperingManager.update_betas(tm, t_scale)
+        out["ladder%d_in" % i], out["ladder%d_betas" % i] = np.array([n, n_post, t_scale]), np.asarray(tm._betas, dtype=np.float64)
+    out["ladder_n"] = np.int64(3)
+    n_sw = 200
+    b1, b2 = rng.uniform(0.05, 1.0, n_sw), rng.uniform(0.05, 1.0, n_sw)
+    l1, l2 = rng.normal(-300.0, 30.0, n_sw), rng.normal(-300.0, 30.0, n_sw)
+    np.random.seed(77)
+    u = np.random.uniform(size=n_sw)
+    np.random.seed(77)
+    acc = np.zeros(n_sw, dtype=bool)
+    for k in range(n_sw):
+        steps = {1: types.SimpleNamespace(beta=b1[k], _llk_index=0), 2: types.SimpleNamespace(beta=b2[k], _llk_index=0)}
+        reg = {}
+        tm = types.SimpleNamespace(worker_a2l=lambda m, source: [m], worker2package=lambda source: {"step": steps[source]},
+                                   register_swap=lambda s1, s2, accepted: reg.update(acc=accepted))
+        rpt.TemperingManager.propose_chain_swap(tm, l1[k], l2[k], 1, 2)
+        acc[k] = reg["acc"]
+    out["swap_b1"], out["swap_b2"], out["swap_l1"], out["swap_l2"], out["swap_u"], out["swap_acc"] = b1, b2, l1, l2, u, acc
 
     np.savez_compressed(os.path.join(HERE, "sampler_golden.npz"), **out)
     print("wrote", os.path.join(HERE, "sampler_golden.npz"), {k: np.asarray(v).shape for k, v in out.items() if k.endswith(("beta", "out", "idx", "scale"))})

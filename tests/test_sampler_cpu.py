@@ -161,3 +161,19 @@ def test_stage_functions_match_the_references_own():
         assert np.array_equal(idx, g["rs%d_idx" % i])
     got = np.array([S.tune_pt_scale(1.3, float(a)) for a in g["pt_acc"]])
     assert np.array_equal(got, g["pt_scale"])
+
+
+def test_pt_ladder_and_swap_rule_match_the_references_own():
+    """The temperature ladder of TemperingManager.update_betas (beat/sampler/pt.py:179-214) and the swap decision of
+    propose_chain_swap (:428-455: alpha = (beta2 - beta1) * (llk1 - llk2), accepted when log(u) < alpha), both run from
+    /root/reference (tests/golden/make_sampler_golden.py): pt_betas is bit-equal, and the vectorised decision pt_sample
+    takes for a pair of chains equals the reference's for the same betas, likelihoods and uniform draws."""
+    g = _sampler_golden()
+    for i in range(int(g["ladder_n"])):
+        n, n_post, t_scale = g["ladder%d_in" % i]
+        assert np.array_equal(S.pt_betas(int(n), int(n_post), float(t_scale)), g["ladder%d_betas" % i])
+    # pt_sample: alpha = (beta_all[b] - beta_all[a]) * (like_all[a] - like_all[b]); acc = log(u) < alpha   (a = chain 1, b = chain 2)
+    alpha = (g["swap_b2"] - g["swap_b1"]) * (g["swap_l1"] - g["swap_l2"])
+    with np.errstate(invalid="ignore"):
+        acc = np.log(g["swap_u"]) < alpha
+    assert np.array_equal(acc, g["swap_acc"]) and 0 < acc.sum() < acc.size
