@@ -46,3 +46,11 @@ def _build_oracle():
     import subprocess
     if not os.path.exists(os.path.join(ROOT, "oracle", "libfsport.so")):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    # libbeatgpu.so is git-ignored: a fresh checkout has to compile it before any test loads it (host-only entries such as
+    # beatgpu_trace_append are used by CPU tests, too).  No-op when the library is up to date; left alone without nvcc.
+    try:
+        from beat_b200.build import build, find_nvcc
+        find_nvcc()
+    except Exception:
+        return
+    build()
