@@ -14,10 +14,17 @@ all-gather of the per-chain llk per step for N > 1).  Synthetic GF libraries are
 
 `value`  : chains/s with q already resident in HBM (device-pointer entry), CUDA events, max over ranks.
 `e2e`    : the same through the host-pointer C-ABI entry: pinned q -> H2D -> kernels -> D2H of logpts+like.
-`roofline`: GF-stacking kernel, algorithmic bytes / its CUDA-event duration vs measured HBM copy peak.
+`roofline`: GF-stacking kernel, algorithmic bytes / its CUDA-event duration (event pairs recorded by the library
+inside the timed loop) vs measured HBM copy peak; `traffic` only from an ncu capture of this very kernel source + blocking.
+`strict_f64`: the same workload with the library stored and every operation done in f64 (the reference's precision).
+`strong` (N > 1): the configuration as BASELINE.json names it -- n_chains = 4000 partitioned over the ranks.
+`sampler_step`: the evaluation inside the lock-step Metropolis step (CUDA graph), also with every record written to trace files.
 `cpu_baseline` / `--impl reference`: the oracle's restatement of the reference CPU path (reference's own compiled
 fast_sweep_ext when oracle/_ref exists, numpy stack_all mode, numpy llk), one chain at a time, fanned out over the
-host cores with a fork pool the way the reference's paripool does -- a reported baseline, not the target.
+host cores with a fork pool the way the reference's paripool does, on a host library with all 17 duration nodes when the
+box has the memory -- a reported baseline, not the target.
+`--config c4 | c5 | c2 | c2llk | c3big`, `--interpolation nearest_neighbor`, `--store f64`, `--noise dense`: the other
+configurations of BASELINE.json / SURVEY 8d for the record (never reported under the C3 metric name).
 """
 import argparse
 import json
